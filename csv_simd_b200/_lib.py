@@ -1,0 +1,86 @@
+"""ctypes binding of libcsvb200.so -- exactly the symbols include/csvb200.h declares.
+
+The library is built in-tree by csv_simd_b200/build.py (nvcc, sm_100a).  If it is missing and
+cannot be built this module raises: there is no CPU fallback anywhere in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+szp = C.POINTER(C.c_size_t)
+vpp = C.POINTER(C.c_void_p)
+
+
+class Range(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("end", C.c_uint64)]
+
+
+# name -> (restype, argtypes); kept in sync with include/csvb200.h (tests/test_abi.py checks it)
+SIGNATURES = {
+    "csvb200_version": (C.c_int, []),
+    "csvb200_status_string": (C.c_char_p, [C.c_int]),
+    "csvb200_ctx_create": (C.c_int, [C.c_int, vpp]),
+    "csvb200_ctx_destroy": (None, [C.c_void_p]),
+    "csvb200_last_error": (C.c_char_p, [C.c_void_p]),
+    "csvb200_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "csvb200_ctx_set_reserve": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "csvb200_ctx_last_build_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "csvb200_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "csvb200_host_alloc": (C.c_int, [C.c_size_t, vpp]),
+    "csvb200_host_free": (C.c_int, [C.c_void_p]),
+    "csvb200_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, vpp]),
+    "csvb200_index_build_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, vpp]),
+    "csvb200_index_build_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, szp]),
+    "csvb200_shard_quote_parity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u32p]),
+    "csvb200_index_build_shard_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64,
+                                                   C.c_int, vpp]),
+    "csvb200_index_sync": (C.c_int, [C.c_void_p]),
+    "csvb200_index_len": (C.c_size_t, [C.c_void_p]),
+    "csvb200_index_end_parity": (C.c_int, [C.c_void_p]),
+    "csvb200_index_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "csvb200_index_copy_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "csvb200_index_free": (None, [C.c_void_p]),
+    "csvb200_tape_init": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, u32p, u64p]),
+    "csvb200_seek_record": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Range), C.POINTER(C.c_int)]),
+    "csvb200_seek_field": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Range), C.POINTER(C.c_int)]),
+    "csvb200_seek_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_seek_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_seek_fields_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_seek_records_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_gather_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                        C.c_size_t]),
+    "csvb200_block_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "csvb200_class_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def so_path() -> str:
+    return _build.SO
+
+
+def load():
+    """Load (building first if stale and nvcc exists) and type the library. Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _build.is_stale():
+        _build.build()
+    if not os.path.exists(_build.SO):
+        raise RuntimeError("libcsvb200.so is missing and could not be built; there is no CPU fallback")
+    lib = C.CDLL(_build.SO)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

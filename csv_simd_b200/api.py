@@ -1,0 +1,235 @@
+"""Thin object layer over the C ABI (include/csvb200.h): Context and StructureIndex.
+
+Everything here forwards to libcsvb200.so; nothing is computed in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .errors import raise_for
+
+BUILD_DEFAULT = 0
+BUILD_KEEP_BYTES = 1
+BUILD_STRICT_MIN64 = 2
+
+NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _as_u8(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        a = data
+        if a.dtype != np.uint8:
+            a = a.view(np.uint8)
+        return np.ascontiguousarray(a)
+    return np.frombuffer(data, dtype=np.uint8)
+
+
+class Context:
+    """csvb200_ctx: one per GPU (process-per-GPU model)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.csvb200_ctx_create(int(device), C.byref(h))
+        raise_for(rc, f"csvb200_ctx_create(device={device}) failed: no usable CUDA device (no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc:
+            raise_for(rc, self._lib.csvb200_last_error(self._h).decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.csvb200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._lib.csvb200_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_reserve(self, num: int, den: int):
+        self._check(self._lib.csvb200_ctx_set_reserve(self._h, num, den))
+
+    def last_build_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.csvb200_ctx_last_build_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self._lib.csvb200_ctx_launch_count(self._h))
+
+    # -- csv -> index ---------------------------------------------------------------------
+    def index_build(self, data, flags: int = BUILD_DEFAULT) -> "StructureIndex":
+        """reader::read (src/reader.rs:150-306) for host bytes."""
+        a = _as_u8(data)
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_build(self._h, a.ctypes.data, a.size, flags, C.byref(h)))
+        return StructureIndex(self, h)
+
+    def index_build_ptr(self, host_ptr: int, n: int, flags: int = BUILD_DEFAULT) -> "StructureIndex":
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_build(self._h, C.c_void_p(host_ptr), n, flags, C.byref(h)))
+        return StructureIndex(self, h)
+
+    def index_build_device(self, dev_ptr: int, n: int, flags: int = BUILD_DEFAULT) -> "StructureIndex":
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_build_device(self._h, C.c_void_p(dev_ptr), n, flags, C.byref(h)))
+        return StructureIndex(self, h)
+
+    def index_build_to_host(self, host_ptr: int, n: int, dst_ptr: int, dst_cap: int) -> int:
+        ln = C.c_size_t()
+        self._check(self._lib.csvb200_index_build_to_host(self._h, C.c_void_p(host_ptr), n, C.c_void_p(dst_ptr),
+                                                          dst_cap, C.byref(ln)))
+        return ln.value
+
+    def shard_quote_parity(self, dev_ptr: int, n: int) -> int:
+        p = C.c_uint32()
+        self._check(self._lib.csvb200_shard_quote_parity(self._h, C.c_void_p(dev_ptr), n, C.byref(p)))
+        return p.value
+
+    def index_build_shard_device(self, dev_ptr: int, n: int, carry_parity: int, global_offset: int,
+                                 emit_sentinel: bool) -> "StructureIndex":
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_build_shard_device(self._h, C.c_void_p(dev_ptr), n, carry_parity,
+                                                               global_offset, int(emit_sentinel), C.byref(h)))
+        return StructureIndex(self, h)
+
+    # -- K1 known-answer exports ------------------------------------------------------------
+    def block_masks(self, data):
+        a = _as_u8(data)
+        nb = (a.size + 63) // 64
+        q = np.zeros(nb, dtype=np.uint64)
+        s = np.zeros(nb, dtype=np.uint64)
+        self._check(self._lib.csvb200_block_masks(self._h, a.ctypes.data, a.size, q.ctypes.data, s.ctypes.data))
+        return q, s
+
+    def class_bytes(self, data) -> np.ndarray:
+        a = _as_u8(data)
+        out = np.zeros(a.size, dtype=np.uint8)
+        self._check(self._lib.csvb200_class_bytes(self._h, a.ctypes.data, a.size, out.ctypes.data))
+        return out
+
+
+class StructureIndex:
+    """csvb200_index: the device-resident StructureIndex(Vec<CodeUnitPos>) (src/stage1.rs:61)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._h = handle
+        self._host = None
+
+    def free(self):
+        if getattr(self, "_h", None):
+            self._lib.csvb200_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+    def sync(self):
+        self.ctx._check(self._lib.csvb200_index_sync(self._h))
+
+    def __len__(self) -> int:
+        self.sync()
+        return int(self._lib.csvb200_index_len(self._h))
+
+    @property
+    def end_parity(self) -> int:
+        self.sync()
+        return int(self._lib.csvb200_index_end_parity(self._h))
+
+    @property
+    def device_ptr(self) -> int:
+        return int(self._lib.csvb200_index_device_ptr(self._h) or 0)
+
+    def to_host(self, out: np.ndarray | None = None) -> np.ndarray:
+        """csvb200_index_copy_out: the index as a host u64 array (what Rust receives as Vec<usize>)."""
+        n = len(self)
+        if out is None:
+            out = np.empty(n, dtype=np.uint64)
+        self.ctx._check(self._lib.csvb200_index_copy_out(self._h, out.ctypes.data, out.size))
+        return out[:n]
+
+    def host(self) -> np.ndarray:
+        if self._host is None:
+            self._host = self.to_host()
+        return self._host
+
+    def copy_out_ptr(self, dst_ptr: int, dst_cap: int):
+        self.ctx._check(self._lib.csvb200_index_copy_out(self._h, C.c_void_p(dst_ptr), dst_cap))
+
+    # -- Tape metadata / lookups ------------------------------------------------------------
+    def tape_init(self, field_cnt: int, crlf: bool):
+        rc_, j = C.c_uint32(), C.c_uint64()
+        rc = self._lib.csvb200_tape_init(self._h, field_cnt, int(crlf), C.byref(rc_), C.byref(j))
+        self.ctx._check(rc)
+        return rc_.value, j.value
+
+    def seek_record(self, r: int):
+        rg, f = _lib.Range(), C.c_int()
+        self.ctx._check(self._lib.csvb200_seek_record(self._h, r & 0xFFFFFFFF, C.byref(rg), C.byref(f)))
+        return (rg.start, rg.end) if f.value else None
+
+    def seek_field(self, r: int, fld: int):
+        rg, f = _lib.Range(), C.c_int()
+        self.ctx._check(self._lib.csvb200_seek_field(self._h, r & 0xFFFFFFFF, fld & 0xFFFFFFFF, C.byref(rg),
+                                                     C.byref(f)))
+        return (rg.start, rg.end) if f.value else None
+
+    def seek_fields(self, rec: np.ndarray, fld: np.ndarray) -> np.ndarray:
+        rec = np.ascontiguousarray(rec, dtype=np.uint32)
+        fld = np.ascontiguousarray(fld, dtype=np.uint32)
+        assert rec.size == fld.size
+        out = np.empty((rec.size, 2), dtype=np.uint64)
+        self.ctx._check(self._lib.csvb200_seek_fields(self._h, rec.ctypes.data, fld.ctypes.data, rec.size,
+                                                      out.ctypes.data))
+        return out
+
+    def seek_records(self, rec: np.ndarray) -> np.ndarray:
+        rec = np.ascontiguousarray(rec, dtype=np.uint32)
+        out = np.empty((rec.size, 2), dtype=np.uint64)
+        self.ctx._check(self._lib.csvb200_seek_records(self._h, rec.ctypes.data, rec.size, out.ctypes.data))
+        return out
+
+    def seek_fields_device(self, d_rec: int, d_fld: int, nq: int, d_out: int):
+        self.ctx._check(self._lib.csvb200_seek_fields_device(self._h, C.c_void_p(d_rec), C.c_void_p(d_fld), nq,
+                                                             C.c_void_p(d_out)))
+
+    def seek_records_device(self, d_rec: int, nq: int, d_out: int):
+        self.ctx._check(self._lib.csvb200_seek_records_device(self._h, C.c_void_p(d_rec), nq, C.c_void_p(d_out)))
+
+    def gather_fields(self, rec: np.ndarray, fld: np.ndarray):
+        rec = np.ascontiguousarray(rec, dtype=np.uint32)
+        fld = np.ascontiguousarray(fld, dtype=np.uint32)
+        offs = np.zeros(rec.size + 1, dtype=np.uint64)
+        # first call sizes the output (CSVB200_ERR_CAPACITY is expected), second call fills it
+        rc = self._lib.csvb200_gather_fields(self._h, rec.ctypes.data, fld.ctypes.data, rec.size, offs.ctypes.data,
+                                             None, 0)
+        if rc not in (0, 9):
+            self.ctx._check(rc)
+        out = np.empty(int(offs[-1]), dtype=np.uint8)
+        if out.size:
+            self.ctx._check(self._lib.csvb200_gather_fields(self._h, rec.ctypes.data, fld.ctypes.data, rec.size,
+                                                            offs.ctypes.data, out.ctypes.data, out.size))
+        return offs, out

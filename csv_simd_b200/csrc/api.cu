@@ -1,0 +1,718 @@
+// api.cu -- the C ABI of libcsvb200 (see include/csvb200.h): context, streams, pinned
+// staging, index objects, Tape metadata and lookup entry points.  Host orchestration only;
+// all compute is in index_build.cu / lookup.cu.  There is deliberately no CPU fallback:
+// every compute entry point returns CSVB200_ERR_CUDA when the device path is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/csvb200.h"
+#include "internal.h"
+
+using namespace csvb200;
+
+namespace {
+constexpr size_t kCells = 4096;              // ring of result cells (4 x u64 each)
+constexpr size_t kCellWords = 4;
+constexpr size_t kStageBytes = 32u << 20;    // pinned staging buffers for pageable input
+constexpr int kStageBufs = 2;
+constexpr size_t kE2eChunk = 64u << 20;      // H2D / kernel / D2H pipeline granularity
+}  // namespace
+
+struct csvb200_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of finished index segments (overlaps H2D)
+    cudaStream_t stream = nullptr;       // the stream work is issued on
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    bool timed = false;
+    uint8_t* d_scratch = nullptr;  // [16 B ticket cell][look-back descriptors]
+    size_t scratch_bytes = 0;
+    uint64_t* d_cells = nullptr;
+    uint64_t* h_cells = nullptr;
+    size_t next_cell = 0;
+    uint8_t* h_stage[kStageBufs] = {nullptr, nullptr};
+    cudaEvent_t stage_free[kStageBufs] = {nullptr, nullptr};
+    uint32_t reserve_num = 1, reserve_den = 3;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+struct csvb200_index {
+    csvb200_ctx* ctx = nullptr;
+    uint64_t* d_index = nullptr;
+    size_t cap = 0;
+    size_t len = 0;
+    int end_parity = 0;
+    bool synced = false;
+    size_t cell = 0;
+    cudaEvent_t done = nullptr;
+    // inputs of the build, kept for the transparent rebuild on capacity overflow
+    const uint8_t* src = nullptr;
+    size_t n = 0;
+    uint32_t carry_parity = 0;
+    uint64_t pos_bias = 0;
+    uint64_t out_base = 1;
+    uint8_t* d_bytes_owned = nullptr;
+    // Tape metadata (TapeCore::init)
+    bool tape_ready = false;
+    uint32_t field_cnt = 0, record_cnt = 0;
+    uint64_t jump = 0;
+    int crlf = 0;
+};
+
+namespace {
+
+int fail(csvb200_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            cudaGetLastError();                                                                 \
+            return fail((ctx), e_ == cudaErrorMemoryAllocation ? CSVB200_ERR_OOM : CSVB200_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
+        }                                                                                       \
+    } while (0)
+
+int ensure_scratch(csvb200_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->scratch_bytes) return CSVB200_OK;
+    size_t nb = std::max(bytes, ctx->scratch_bytes * 2);
+    nb = (nb + 4095) & ~size_t(4095);
+    if (ctx->d_scratch) CU_TRY(ctx, cudaFreeAsync(ctx->d_scratch, ctx->stream));
+    ctx->d_scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    CU_TRY(ctx, cudaMallocAsync((void**)&ctx->d_scratch, nb, ctx->stream));
+    ctx->scratch_bytes = nb;
+    return CSVB200_OK;
+}
+
+size_t initial_cap(const csvb200_ctx* ctx, size_t n)
+{
+    return (size_t)((unsigned __int128)n * ctx->reserve_num / ctx->reserve_den) + 4096;
+}
+
+// enqueue one build of idx->src[0..n) into idx->d_index (capacity idx->cap)
+int enqueue_build(csvb200_index* idx, bool timed)
+{
+    csvb200_ctx* ctx = idx->ctx;
+    const size_t n = idx->n;
+    const uint64_t num_tiles = (n + kTileBytes - 1) / kTileBytes;
+    if (num_tiles > 0xffffffffull) return fail(ctx, CSVB200_ERR_INVALID_ARG, "input too large for one launch");
+    uint64_t* d_cell = ctx->d_cells + idx->cell * kCellWords;
+    uint64_t* h_cell = ctx->h_cells + idx->cell * kCellWords;
+    if (idx->out_base == 1 && idx->cap > 0) CU_TRY(ctx, cudaMemsetAsync(idx->d_index, 0, 8, ctx->stream));  // sentinel
+    if (num_tiles == 0) {
+        h_cell[0] = 0;
+        h_cell[1] = idx->carry_parity;
+    } else {
+        const size_t sbytes = 16 + num_tiles * sizeof(uint64_t);
+        int rc = ensure_scratch(ctx, sbytes);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, ctx->stream));
+        BuildParams p{};
+        p.in = idx->src;
+        p.n = n;
+        p.index = idx->d_index;
+        p.cap = idx->cap;
+        p.out_base = idx->out_base;
+        p.pos_bias = idx->pos_bias;
+        p.carry = nullptr;
+        p.carry_count = 0;
+        p.carry_parity = idx->carry_parity;
+        p.num_tiles = (uint32_t)num_tiles;
+        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
+        p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 16);
+        p.result = d_cell;
+        if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+        CU_TRY(ctx, launch_index_build(p, ctx->stream));
+        ctx->launches += 1;
+        if (timed) {
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
+            ctx->timed = true;
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU_TRY(ctx, cudaEventRecord(idx->done, ctx->stream));
+    idx->synced = false;
+    return CSVB200_OK;
+}
+
+int new_index(csvb200_ctx* ctx, csvb200_index** out)
+{
+    csvb200_index* idx = new (std::nothrow) csvb200_index();
+    if (!idx) return fail(ctx, CSVB200_ERR_OOM, "host allocation failed");
+    idx->ctx = ctx;
+    idx->cell = ctx->next_cell;
+    ctx->next_cell = (ctx->next_cell + 1) % kCells;
+    cudaError_t e = cudaEventCreateWithFlags(&idx->done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete idx;
+        return fail(ctx, CSVB200_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+    }
+    *out = idx;
+    return CSVB200_OK;
+}
+
+int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity, uint64_t pos_bias,
+                        int emit_sentinel, csvb200_index** out)
+{
+    if (!ctx || !out || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    if ((reinterpret_cast<uintptr_t>(dev_bytes) & 15u) != 0)
+        return fail(ctx, CSVB200_ERR_INVALID_ARG, "device input must be 16-byte aligned");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    csvb200_index* idx = nullptr;
+    int rc = new_index(ctx, &idx);
+    if (rc) return rc;
+    idx->src = static_cast<const uint8_t*>(dev_bytes);
+    idx->n = n;
+    idx->carry_parity = carry_parity & 1u;
+    idx->pos_bias = pos_bias;
+    idx->out_base = emit_sentinel ? 1 : 0;
+    idx->cap = initial_cap(ctx, n);
+    cudaError_t e = cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        csvb200_index_free(idx);
+        return fail(ctx, CSVB200_ERR_OOM, std::string("index allocation: ") + cudaGetErrorString(e));
+    }
+    rc = enqueue_build(idx, true);
+    if (rc) {
+        csvb200_index_free(idx);
+        return rc;
+    }
+    *out = idx;
+    return CSVB200_OK;
+}
+
+// host -> device copy of n bytes; pinned sources go straight to cudaMemcpyAsync, pageable ones
+// through the context's pinned staging ring.
+int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n)
+{
+    if (n == 0) return CSVB200_OK;
+    cudaPointerAttributes attr{};
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h_src) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        CU_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, ctx->stream));
+        return CSVB200_OK;
+    }
+    for (int b = 0; b < kStageBufs; ++b) {
+        if (!ctx->h_stage[b]) {
+            CU_TRY(ctx, cudaHostAlloc((void**)&ctx->h_stage[b], kStageBytes, cudaHostAllocDefault));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->stage_free[b], cudaEventDisableTiming));
+        }
+    }
+    size_t off = 0;
+    int b = 0;
+    while (off < n) {
+        const size_t len = std::min(kStageBytes, n - off);
+        CU_TRY(ctx, cudaEventSynchronize(ctx->stage_free[b]));
+        std::memcpy(ctx->h_stage[b], h_src + off, len);
+        CU_TRY(ctx, cudaMemcpyAsync(d_dst + off, ctx->h_stage[b], len, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaEventRecord(ctx->stage_free[b], ctx->stream));
+        off += len;
+        b = (b + 1) % kStageBufs;
+    }
+    return CSVB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int csvb200_version(void) { return CSVB200_VERSION; }
+
+const char* csvb200_status_string(int s)
+{
+    switch (s) {
+    case CSVB200_OK: return "ok";
+    case CSVB200_ERR_INVALID_ARG: return "invalid argument";
+    case CSVB200_ERR_INVALID_STATE: return "Invalid state";
+    case CSVB200_ERR_INVALID_CSV_FORMAT: return "Unsupported csv structure: likely variable number of fields";
+    case CSVB200_ERR_MISSING_VALUE: return "Missing a value";
+    case CSVB200_ERR_IO: return "io error";
+    case CSVB200_ERR_CUDA: return "CUDA error";
+    case CSVB200_ERR_OOM: return "out of memory";
+    case CSVB200_ERR_INPUT_TOO_SMALL: return "input shorter than 64 bytes";
+    case CSVB200_ERR_CAPACITY: return "destination capacity too small";
+    case CSVB200_ERR_OUT_OF_BOUNDS: return "index slot out of bounds";
+    default: return "unknown status";
+    }
+}
+
+int csvb200_ctx_create(int device, csvb200_ctx** out)
+{
+    if (!out) return CSVB200_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return CSVB200_ERR_CUDA;  // no CPU fallback by design
+    }
+    csvb200_ctx* ctx = new (std::nothrow) csvb200_ctx();
+    if (!ctx) return CSVB200_ERR_OOM;
+    ctx->device = device;
+    auto bail = [&](cudaError_t) {
+        cudaGetLastError();
+        csvb200_ctx_destroy(ctx);
+        return (int)CSVB200_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    ctx->stream = ctx->own_stream;
+    if ((e = cudaEventCreate(&ctx->ev_k0)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&ctx->ev_k1)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc((void**)&ctx->d_cells, kCells * kCellWords * sizeof(uint64_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaHostAlloc((void**)&ctx->h_cells, kCells * kCellWords * sizeof(uint64_t), cudaHostAllocDefault)) !=
+        cudaSuccess)
+        return bail(e);
+    // keep freed blocks in the stream-ordered pool so per-build allocations are reused, not re-mapped
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    *out = ctx;
+    return CSVB200_OK;
+}
+
+void csvb200_ctx_destroy(csvb200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_cells) cudaFree(ctx->d_cells);
+    if (ctx->h_cells) cudaFreeHost(ctx->h_cells);
+    for (int b = 0; b < kStageBufs; ++b) {
+        if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+        if (ctx->stage_free[b]) cudaEventDestroy(ctx->stage_free[b]);
+    }
+    if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+    if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+const char* csvb200_last_error(const csvb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int csvb200_ctx_set_stream(csvb200_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return CSVB200_ERR_INVALID_ARG;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return CSVB200_OK;
+}
+
+int csvb200_ctx_set_reserve(csvb200_ctx* ctx, uint32_t num, uint32_t den)
+{
+    if (!ctx || den == 0) return fail(ctx, CSVB200_ERR_INVALID_ARG, "bad reserve ratio");
+    ctx->reserve_num = num;
+    ctx->reserve_den = den;
+    return CSVB200_OK;
+}
+
+int csvb200_ctx_last_build_ms(csvb200_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return CSVB200_ERR_INVALID_ARG;
+    if (!ctx->timed) return fail(ctx, CSVB200_ERR_INVALID_STATE, "no timed build yet");
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev_k1));
+    CU_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+    return CSVB200_OK;
+}
+
+uint64_t csvb200_ctx_launch_count(const csvb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int csvb200_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return CSVB200_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? CSVB200_ERR_OOM : CSVB200_ERR_CUDA;
+    }
+    return CSVB200_OK;
+}
+
+int csvb200_host_free(void* p)
+{
+    if (!p) return CSVB200_OK;
+    return cudaFreeHost(p) == cudaSuccess ? CSVB200_OK : CSVB200_ERR_CUDA;
+}
+
+int csvb200_index_build_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t flags, csvb200_index** out)
+{
+    if (ctx && (flags & CSVB200_BUILD_STRICT_MIN64) && n < 64)
+        return fail(ctx, CSVB200_ERR_INPUT_TOO_SMALL, "n < 64: the reference panics on this input");
+    return build_device_common(ctx, dev_bytes, n, 0u, 0ull, 1, out);
+}
+
+int csvb200_index_build_shard_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity,
+                                     uint64_t global_offset, int emit_sentinel, csvb200_index** out)
+{
+    return build_device_common(ctx, dev_bytes, n, carry_parity, global_offset, emit_sentinel, out);
+}
+
+int csvb200_index_build(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint32_t flags, csvb200_index** out)
+{
+    if (!ctx || !out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    if ((flags & CSVB200_BUILD_STRICT_MIN64) && n < 64)
+        return fail(ctx, CSVB200_ERR_INPUT_TOO_SMALL, "n < 64: the reference panics on this input");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    uint8_t* d_bytes = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, ctx->stream));
+    int rc = upload(ctx, d_bytes, host_bytes, n);
+    csvb200_index* idx = nullptr;
+    if (!rc) rc = build_device_common(ctx, d_bytes, n, 0u, 0ull, 1, &idx);
+    if (!rc) rc = csvb200_index_sync(idx);  // resolves a capacity overflow while the bytes are still here
+    if (rc) {
+        if (idx) csvb200_index_free(idx);
+        cudaFreeAsync(d_bytes, ctx->stream);
+        return rc;
+    }
+    if (flags & CSVB200_BUILD_KEEP_BYTES) {
+        idx->d_bytes_owned = d_bytes;
+    } else {
+        CU_TRY(ctx, cudaFreeAsync(d_bytes, ctx->stream));
+        idx->src = nullptr;
+    }
+    *out = idx;
+    return CSVB200_OK;
+}
+
+int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap,
+                                size_t* len_out)
+{
+    if (!ctx || !len_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    csvb200_index* idx = nullptr;
+    int rc = csvb200_index_build(ctx, host_bytes, n, CSVB200_BUILD_DEFAULT, &idx);
+    if (rc) return rc;
+    *len_out = idx->len;
+    rc = idx->len <= dst_cap ? csvb200_index_copy_out(idx, dst, dst_cap)
+                             : fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    csvb200_index_free(idx);
+    return rc;
+}
+
+int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t* parity_out)
+{
+    if (!ctx || !parity_out || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    if ((reinterpret_cast<uintptr_t>(dev_bytes) & 15u) != 0)
+        return fail(ctx, CSVB200_ERR_INVALID_ARG, "device input must be 16-byte aligned");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t cell = ctx->next_cell;
+    ctx->next_cell = (ctx->next_cell + 1) % kCells;
+    uint64_t* d_cell = ctx->d_cells + cell * kCellWords;
+    uint64_t* h_cell = ctx->h_cells + cell * kCellWords;
+    CU_TRY(ctx, cudaMemsetAsync(d_cell, 0, sizeof(uint64_t), ctx->stream));
+    CU_TRY(ctx, launch_quote_parity(static_cast<const uint8_t*>(dev_bytes), n, reinterpret_cast<uint32_t*>(d_cell),
+                                    ctx->stream));
+    if (n) ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *parity_out = (uint32_t)(h_cell[0] & 1u);
+    return CSVB200_OK;
+}
+
+int csvb200_index_sync(csvb200_index* idx)
+{
+    if (!idx) return CSVB200_ERR_INVALID_ARG;
+    if (idx->synced) return CSVB200_OK;
+    csvb200_ctx* ctx = idx->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CU_TRY(ctx, cudaEventSynchronize(idx->done));
+        const uint64_t* h_cell = ctx->h_cells + idx->cell * kCellWords;
+        const size_t len = (size_t)(idx->out_base + h_cell[0]);
+        idx->end_parity = (int)(h_cell[1] & 1u);
+        if (len <= idx->cap) {
+            idx->len = len;
+            idx->synced = true;
+            return CSVB200_OK;
+        }
+        // capacity overflow (denser than the reserve heuristic): rebuild with the exact size
+        if (!idx->src) return fail(ctx, CSVB200_ERR_INVALID_STATE, "index overflow and input no longer available");
+        CU_TRY(ctx, cudaFreeAsync(idx->d_index, ctx->stream));
+        idx->d_index = nullptr;
+        idx->cap = len + 2;
+        CU_TRY(ctx, cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream));
+        int rc = enqueue_build(idx, true);
+        if (rc) return rc;
+    }
+    return fail(ctx, CSVB200_ERR_CUDA, "index rebuild did not converge");
+}
+
+size_t csvb200_index_len(csvb200_index* idx)
+{
+    if (!idx || csvb200_index_sync(idx) != CSVB200_OK) return 0;
+    return idx->len;
+}
+
+int csvb200_index_end_parity(csvb200_index* idx)
+{
+    if (!idx || csvb200_index_sync(idx) != CSVB200_OK) return -1;
+    return idx->end_parity;
+}
+
+const uint64_t* csvb200_index_device_ptr(csvb200_index* idx)
+{
+    if (!idx || csvb200_index_sync(idx) != CSVB200_OK) return nullptr;
+    return idx->d_index;
+}
+
+int csvb200_index_copy_out(csvb200_index* idx, uint64_t* dst, size_t dst_cap)
+{
+    if (!idx || !dst) return CSVB200_ERR_INVALID_ARG;
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    if (idx->len > dst_cap) return fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    CU_TRY(ctx, cudaMemcpyAsync(dst, idx->d_index, idx->len * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CSVB200_OK;
+}
+
+void csvb200_index_free(csvb200_index* idx)
+{
+    if (!idx) return;
+    csvb200_ctx* ctx = idx->ctx;
+    cudaSetDevice(ctx->device);
+    if (idx->d_index) cudaFreeAsync(idx->d_index, ctx->stream);
+    if (idx->d_bytes_owned) cudaFreeAsync(idx->d_bytes_owned, ctx->stream);
+    if (idx->done) cudaEventDestroy(idx->done);
+    cudaGetLastError();
+    delete idx;
+}
+
+int csvb200_tape_init(csvb200_index* idx, uint32_t field_cnt, int crlf, uint32_t* record_cnt, uint64_t* jump)
+{
+    if (!idx) return CSVB200_ERR_INVALID_ARG;
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    const uint64_t j = crlf ? (uint64_t)field_cnt + 1 : (uint64_t)field_cnt;  // src/tape.rs:318-321
+    if (j == 0 || idx->len == 0) return fail(ctx, CSVB200_ERR_INVALID_ARG, "field_cnt must be >= 1");
+    idx->field_cnt = field_cnt;
+    idx->crlf = crlf ? 1 : 0;
+    idx->jump = j;
+    idx->record_cnt = (uint32_t)((idx->len - 1) / j);  // src/tape.rs:323-325
+    idx->tape_ready = true;
+    if (record_cnt) *record_cnt = idx->record_cnt;
+    if (jump) *jump = j;
+    if ((idx->len - 1) % j != 0)  // src/tape.rs:327,342-344
+        return fail(ctx, CSVB200_ERR_INVALID_CSV_FORMAT, csvb200_status_string(CSVB200_ERR_INVALID_CSV_FORMAT));
+    return CSVB200_OK;
+}
+
+static int seek_device(csvb200_index* idx, const uint32_t* d_rec, const uint32_t* d_fld, size_t nq,
+                       csvb200_range* d_out, uint32_t* d_oob)
+{
+    csvb200_ctx* ctx = idx->ctx;
+    LookupParams p{};
+    p.index = idx->d_index;
+    p.index_len = idx->len;
+    p.record_cnt = idx->record_cnt;
+    p.field_cnt = idx->field_cnt;
+    p.row_size = (uint32_t)idx->jump;
+    p.rec = d_rec;
+    p.fld = d_fld;
+    p.nq = nq;
+    p.ranges = reinterpret_cast<uint64_t*>(d_out);
+    p.oob = d_oob;
+    CU_TRY(ctx, launch_seek(p, ctx->stream));
+    if (nq) ctx->launches += 1;
+    return CSVB200_OK;
+}
+
+static int seek_prepare(csvb200_index* idx)
+{
+    if (!idx) return CSVB200_ERR_INVALID_ARG;
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    if (!idx->tape_ready)  // RecordSource::record_cnt() == None -> InvalidState (record_source.rs:77-79)
+        return fail(idx->ctx, CSVB200_ERR_INVALID_STATE, "csvb200_tape_init has not been called");
+    CU_TRY(idx->ctx, cudaSetDevice(idx->ctx->device));
+    return CSVB200_OK;
+}
+
+static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fld, size_t nq, csvb200_range* out)
+{
+    int rc = seek_prepare(idx);
+    if (rc) return rc;
+    if (nq == 0) return CSVB200_OK;
+    if (!rec || !out) return fail(idx->ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    csvb200_ctx* ctx = idx->ctx;
+    uint32_t *d_rec = nullptr, *d_fld = nullptr, *d_oob = nullptr;
+    csvb200_range* d_out = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_rec, nq * sizeof(uint32_t), ctx->stream));
+    if (fld) CU_TRY(ctx, cudaMallocAsync((void**)&d_fld, nq * sizeof(uint32_t), ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_out, nq * sizeof(csvb200_range), ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_oob, sizeof(uint32_t), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_oob, 0, sizeof(uint32_t), ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_rec, rec, nq * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (fld) CU_TRY(ctx, cudaMemcpyAsync(d_fld, fld, nq * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    rc = seek_device(idx, d_rec, d_fld, nq, d_out, d_oob);
+    uint32_t oob = 0;
+    if (!rc) {
+        CU_TRY(ctx, cudaMemcpyAsync(out, d_out, nq * sizeof(csvb200_range), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(&oob, d_oob, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFreeAsync(d_rec, ctx->stream);
+    if (d_fld) cudaFreeAsync(d_fld, ctx->stream);
+    cudaFreeAsync(d_out, ctx->stream);
+    cudaFreeAsync(d_oob, ctx->stream);
+    if (rc) return rc;
+    if (oob) return fail(ctx, CSVB200_ERR_OUT_OF_BOUNDS, "lookup slot past the end of the index");
+    return CSVB200_OK;
+}
+
+int csvb200_seek_records(csvb200_index* idx, const uint32_t* rec, size_t nq, csvb200_range* out)
+{
+    return seek_host(idx, rec, nullptr, nq, out);
+}
+
+int csvb200_seek_fields(csvb200_index* idx, const uint32_t* rec, const uint32_t* fld, size_t nq, csvb200_range* out)
+{
+    if (idx && nq && !fld) return fail(idx->ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    return seek_host(idx, rec, fld, nq, out);
+}
+
+int csvb200_seek_record(csvb200_index* idx, uint32_t record_idx, csvb200_range* out, int* found)
+{
+    if (!out || !found) return CSVB200_ERR_INVALID_ARG;
+    int rc = seek_host(idx, &record_idx, nullptr, 1, out);
+    if (!rc) *found = out->start != UINT64_MAX;
+    return rc;
+}
+
+int csvb200_seek_field(csvb200_index* idx, uint32_t record_idx, uint32_t field_idx, csvb200_range* out, int* found)
+{
+    if (!out || !found) return CSVB200_ERR_INVALID_ARG;
+    int rc = seek_host(idx, &record_idx, &field_idx, 1, out);
+    if (!rc) *found = out->start != UINT64_MAX;
+    return rc;
+}
+
+int csvb200_seek_fields_device(csvb200_index* idx, const uint32_t* d_rec, const uint32_t* d_fld, size_t nq,
+                               csvb200_range* d_out)
+{
+    int rc = seek_prepare(idx);
+    if (rc) return rc;
+    if (nq && (!d_rec || !d_fld || !d_out)) return fail(idx->ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    // out-of-bounds slots are reported as None on this asynchronous path
+    return seek_device(idx, d_rec, d_fld, nq, d_out, reinterpret_cast<uint32_t*>(idx->ctx->d_cells + (kCells - 1) * kCellWords));
+}
+
+int csvb200_seek_records_device(csvb200_index* idx, const uint32_t* d_rec, size_t nq, csvb200_range* d_out)
+{
+    int rc = seek_prepare(idx);
+    if (rc) return rc;
+    if (nq && (!d_rec || !d_out)) return fail(idx->ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    return seek_device(idx, d_rec, nullptr, nq, d_out, reinterpret_cast<uint32_t*>(idx->ctx->d_cells + (kCells - 1) * kCellWords));
+}
+
+int csvb200_gather_fields(csvb200_index* idx, const uint32_t* rec, const uint32_t* fld, size_t nq,
+                          uint64_t* out_offsets, uint8_t* out, size_t out_cap)
+{
+    int rc = seek_prepare(idx);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    if (!idx->d_bytes_owned && !idx->src)
+        return fail(ctx, CSVB200_ERR_INVALID_STATE, "index was built without CSVB200_BUILD_KEEP_BYTES");
+    if (!out_offsets || (nq && (!rec || !fld))) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    out_offsets[0] = 0;
+    if (nq == 0) return CSVB200_OK;
+    std::vector<csvb200_range> ranges(nq);
+    rc = seek_host(idx, rec, fld, nq, ranges.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < nq; ++i) {
+        const csvb200_range& r = ranges[i];
+        const uint64_t len = (r.start == UINT64_MAX || r.end < r.start) ? 0 : r.end - r.start;
+        out_offsets[i + 1] = out_offsets[i] + len;
+    }
+    const uint64_t total = out_offsets[nq];
+    if (total > out_cap) return fail(ctx, CSVB200_ERR_CAPACITY, "gather destination too small");
+    if (total == 0) return CSVB200_OK;
+    if (!out) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    uint64_t *d_ranges = nullptr, *d_off = nullptr;
+    uint8_t* d_out = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_ranges, nq * sizeof(csvb200_range), ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_off, (nq + 1) * sizeof(uint64_t), ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_out, total, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_ranges, ranges.data(), nq * sizeof(csvb200_range), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_off, out_offsets, (nq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* bytes = idx->d_bytes_owned ? idx->d_bytes_owned : idx->src;
+    CU_TRY(ctx, launch_gather_bytes(bytes, d_ranges, d_off, nq, d_out, ctx->stream));
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(d_ranges, ctx->stream);
+    cudaFreeAsync(d_off, ctx->stream);
+    cudaFreeAsync(d_out, ctx->stream);
+    return CSVB200_OK;
+}
+
+int csvb200_block_masks(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* quote_words,
+                        uint64_t* sep_words)
+{
+    if (!ctx || (n && (!host_bytes || !quote_words || !sep_words))) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return CSVB200_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (n + 63) / 64;
+    uint8_t* d_in = nullptr;
+    uint64_t *d_q = nullptr, *d_s = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_in, n, ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_q, nb * 8, ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_s, nb * 8, ctx->stream));
+    int rc = upload(ctx, d_in, host_bytes, n);
+    if (rc) return rc;
+    CU_TRY(ctx, launch_block_masks(d_in, n, d_q, d_s, ctx->stream));
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(quote_words, d_q, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(sep_words, d_s, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(d_in, ctx->stream);
+    cudaFreeAsync(d_q, ctx->stream);
+    cudaFreeAsync(d_s, ctx->stream);
+    return CSVB200_OK;
+}
+
+int csvb200_class_bytes(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint8_t* out)
+{
+    if (!ctx || (n && (!host_bytes || !out))) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return CSVB200_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_in, n, ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_out, n, ctx->stream));
+    int rc = upload(ctx, d_in, host_bytes, n);
+    if (rc) return rc;
+    CU_TRY(ctx, launch_class_bytes(d_in, n, d_out, ctx->stream));
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(d_in, ctx->stream);
+    cudaFreeAsync(d_out, ctx->stream);
+    return CSVB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,403 @@
+// index_build.cu -- fused single-pass CSV structural index build for sm_100a.
+//
+// Replaces, in ONE kernel and one pass over the input (traffic = N + 8E):
+//   reader::read            src/reader.rs:150-306      (64-byte block loop, tail padding, carries)
+//   SimdInput::structure    src/avx/stage1.rs:193-407  (classify, bit-pack, clmul prefix-XOR, carry, mask)
+//   Stage1::crush_set_bits  src/stage1.rs:162-296      (tzcnt/blsr extraction into the growing Vec<usize>)
+//
+// The two serial dependencies of the reference loop -- the 1-bit `inside_str`
+// carry (reader.rs:218, stage1.rs:397,407) and the running `array_idx`
+// (reader.rs:217, stage1.rs:176-177,292) -- become ONE decoupled look-back over
+// the monoid (p, c0, c1):
+//   p  = quote parity of a tile
+//   c0 = number of separators outside quotes if the tile is entered outside quotes
+//   c1 = the same if the tile is entered inside quotes
+//   (p1,a0,a1) o (p2,b0,b1) = (p1^p2, a0 + (p1 ? b1 : b0), a1 + (p1 ? b0 : b1))
+// so every tile learns both its carry-in parity and its output base from the
+// same chain and the input is read exactly once.
+//
+// Per tile (16 KiB, 256 threads x 64 B):
+//   1. coalesced 128-bit loads -> shared memory in the TMA SWIZZLE_128B pattern,
+//      so each thread can read back its own 64 contiguous bytes conflict-free;
+//   2. bit-sliced classification (bitslice.cuh) -> 32-bit quote / separator masks;
+//   3. in-word prefix-XOR (shift-xor), thread parities via one ballot, packed
+//      (c0 | total) warp scan with shuffles, 8-entry warp-aggregate scan;
+//   4. warp-parallel decoupled look-back (single u64 descriptor per tile);
+//   5. ordered compaction: every thread expands its mask into 16-bit tile-relative
+//      offsets in shared memory at its scanned slot, then the CTA streams the tile's
+//      run out as full 16-byte stores (2 entries) of pos_bias + tile_base + offset.
+#include "bitslice.cuh"
+#include "internal.h"
+
+namespace csvb200 {
+
+namespace {
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_stream_128(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_128(void* p, uint64_t a, uint64_t b)
+{
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+struct WarpState {
+    uint32_t par;   // quote parity of the warps before this one (relative to tile start)
+    uint32_t off0;  // entries emitted by those warps if the tile is entered outside quotes
+    uint32_t off1;  // ... if entered inside quotes
+};
+
+// Shared memory: the input tile (16 KiB) is dead once every thread has pulled its
+// 64 bytes into registers, so the 16-bit staging area of the compaction (worst
+// case one entry per byte = 32 KiB, +1 slot for 16-byte store alignment) aliases it.
+struct __align__(1024) Smem {
+    union {
+        uint8_t in[kTileBytes];
+        uint16_t stage[kTileBytes + 8];
+    };
+    uint32_t warp_agg[kWarps];
+    WarpState warp_state[kWarps];
+    uint32_t tile;
+    uint32_t pin;
+    uint32_t tot0, tot1;
+    uint64_t base;
+};
+
+__global__ void __launch_bounds__(kThreads, 4) index_build_kernel(const BuildParams p)
+{
+    __shared__ Smem sm;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+
+    // dynamic tile id: a tile only ever waits on tiles whose CTAs already started
+    if (tid == 0) sm.tile = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    const uint64_t tile_off = (uint64_t)tile * kTileBytes;
+
+    // ---- 1. global -> shared, coalesced, swizzled (chunk' = chunk ^ (row & 7)) ----
+    {
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t c = tid + kThreads * i;
+            const uint64_t goff = tile_off + 16ull * c;
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (goff + 16 <= p.n) {
+                v[i] = ldg_stream_128(p.in + goff);
+            } else if (goff < p.n) {
+                // the reference zero-pads the final block (avx/stage1.rs:54-57,64-88)
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                const uint32_t rem = (uint32_t)(p.n - goff);
+                for (uint32_t b = 0; b < rem; ++b) w[b >> 2] |= (uint32_t)p.in[goff + b] << (8 * (b & 3));
+                v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t c = tid + kThreads * i;
+            const uint32_t pc = c ^ ((c >> 3) & 7u);
+            *reinterpret_cast<uint4*>(sm.in + 16u * pc) = v[i];
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. each thread: its 64 contiguous bytes -> quote / separator masks ----
+    uint32_t q0, s0, q1, s1;
+    {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t pc = (4u * tid + i) ^ ((tid >> 1) & 7u);
+            const uint4 v = *reinterpret_cast<const uint4*>(sm.in + 16u * pc);
+            w[4 * i + 0] = v.x;
+            w[4 * i + 1] = v.y;
+            w[4 * i + 2] = v.z;
+            w[4 * i + 3] = v.w;
+        }
+        const Masks32 m0 = classify32(w);
+        const Masks32 m1 = classify32(w + 8);
+        q0 = m0.quote;
+        s0 = m0.sep;
+        q1 = m1.quote;
+        s1 = m1.sep;
+    }
+
+    // ---- 3. quote regions inside the warp (relative to the warp start) ----
+    // x = inclusive prefix-XOR of the quote bits: opening quote bit = 1, closing = 0,
+    // exactly the reference's string_mask (avx/stage1.rs:397).
+    uint32_t x0 = 0u, x1 = 0u, warp_par = 0u;
+    if (__any_sync(0xffffffffu, (q0 | q1) != 0u)) {
+        x0 = prefix_xor32(q0);
+        x1 = prefix_xor32(q1) ^ (0u - (x0 >> 31));
+        const uint32_t bal = __ballot_sync(0xffffffffu, (x1 >> 31) != 0u);
+        const uint32_t lane_in = __popc(bal & ((1u << lane) - 1u)) & 1u;
+        warp_par = __popc(bal) & 1u;
+        const uint32_t flip = 0u - lane_in;
+        x0 ^= flip;
+        x1 ^= flip;
+    }
+    // counts under "warp entered outside quotes" (a0) and the hypothesis-free total (tt)
+    const uint32_t a0 = __popc(s0 & ~x0) + __popc(s1 & ~x1);
+    const uint32_t tt = __popc(s0) + __popc(s1);
+    const uint32_t packed = a0 | (tt << 16);
+    uint32_t inc = packed;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += v;
+    }
+    const uint32_t exc = inc - packed;
+    if (lane == 31) sm.warp_agg[warp] = inc | (warp_par << 31);
+    __syncthreads();  // also: every thread is done reading sm.in
+
+    // ---- 4. warp 0: scan the 8 warp aggregates, publish, look back ----
+    if (warp == 0) {
+        uint32_t par = 0u, o0 = 0u, o1 = 0u;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t v = sm.warp_agg[w];
+            const uint32_t wa0 = v & 0x7fffu, wt = (v >> 16) & 0x7fffu, wa1 = wt - wa0;
+            if (lane == 0) {
+                sm.warp_state[w].par = par;
+                sm.warp_state[w].off0 = o0;
+                sm.warp_state[w].off1 = o1;
+            }
+            o0 += par ? wa1 : wa0;
+            o1 += par ? wa0 : wa1;
+            par ^= v >> 31;
+        }
+        // (par, o0, o1) is the tile aggregate
+        if (lane == 0)
+            st_relaxed_u64(p.desc + tile, kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
+
+        // virtual predecessor of tile 0: the carry entering this launch
+        uint64_t carry_count = p.carry_count;
+        uint32_t carry_parity = p.carry_parity;
+        if (p.carry != nullptr) {
+            carry_count = p.carry[0];
+            carry_parity = (uint32_t)p.carry[1] & 1u;
+        }
+        const uint64_t virt = kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
+
+        // suffix composite S of the tiles already absorbed (those nearest to us)
+        uint32_t sp = 0u;
+        uint64_t sc0 = 0ull, sc1 = 0ull;
+        int64_t idx = (int64_t)tile - 1 - (int64_t)lane;
+        uint32_t pin;
+        uint64_t base;
+        while (true) {
+            const uint64_t d = idx >= 0 ? ld_relaxed_u64(p.desc + idx) : virt;
+            const uint32_t status = (uint32_t)(d >> 62);
+            const uint32_t pref = __ballot_sync(0xffffffffu, status == 2u);
+            const uint32_t inval = __ballot_sync(0xffffffffu, status == 0u);
+            const uint32_t lp = pref ? (uint32_t)(__ffs(pref) - 1) : 32u;       // nearest prefix lane
+            const uint32_t need = lp >= 32u ? 0xffffffffu : ((1u << lp) - 1u);  // lanes that must be aggregates
+            if (inval & need) continue;                                         // predecessor not published yet
+            const bool in_win = lane < lp;
+            const uint32_t pj = in_win ? (uint32_t)((d >> 61) & 1ull) : 0u;
+            const uint32_t c0j = (uint32_t)(d & 0xfffffull), c1j = (uint32_t)((d >> 20) & 0xfffffull);
+            const uint32_t bp = __ballot_sync(0xffffffffu, pj != 0u);
+            // parity accumulated by the window tiles EARLIER than mine (= higher lanes)
+            const uint32_t rel = __popc(bp & (0xfffffffeu << lane)) & 1u;
+            const uint32_t w0j = in_win ? (rel ? c1j : c0j) : 0u;
+            const uint32_t w1j = in_win ? (rel ? c0j : c1j) : 0u;
+            const uint32_t W0 = __reduce_add_sync(0xffffffffu, w0j);
+            const uint32_t W1 = __reduce_add_sync(0xffffffffu, w1j);
+            const uint32_t Wp = __popc(bp) & 1u;
+            // S <- W o S   (window is earlier in the file than everything absorbed so far)
+            const uint64_t n0 = (uint64_t)W0 + (Wp ? sc1 : sc0);
+            const uint64_t n1 = (uint64_t)W1 + (Wp ? sc0 : sc1);
+            sc0 = n0;
+            sc1 = n1;
+            sp ^= Wp;
+            if (pref) {
+                const uint64_t pd = __shfl_sync(0xffffffffu, d, (int)lp);
+                const uint32_t P = (uint32_t)((pd >> 61) & 1ull);
+                pin = P ^ sp;
+                base = (pd & kCountMask) + (P ? sc1 : sc0);
+                break;
+            }
+            idx -= 32;
+        }
+        if (lane == 0) {
+            const uint32_t pend = pin ^ par;
+            const uint64_t cend = base + (pin ? o1 : o0);
+            st_relaxed_u64(p.desc + tile, kStatusPrefix | (pend ? kParityBit : 0ull) | (cend & kCountMask));
+            sm.pin = pin;
+            sm.base = base;
+            sm.tot0 = o0;
+            sm.tot1 = o1;
+            if (tile == p.num_tiles - 1) {
+                p.result[0] = cend;
+                p.result[1] = pend;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 5. ordered compaction ----
+    const uint32_t pin = sm.pin;
+    const uint64_t base = sm.base;
+    const uint32_t cnt = pin ? sm.tot1 : sm.tot0;
+    const uint64_t g0 = p.out_base + base;              // slot of this tile's first entry
+    const uint32_t head = (uint32_t)(g0 & 1ull);         // keep even slots on even staging indices
+    {
+        const WarpState ws = sm.warp_state[warp];
+        const uint32_t h = pin ^ ws.par;                 // parity entering this warp
+        const uint32_t ex_a0 = exc & 0x7fffu, ex_tt = (exc >> 16) & 0x7fffu;
+        uint32_t slot = head + (pin ? ws.off1 : ws.off0) + (h ? ex_tt - ex_a0 : ex_a0);
+        const uint32_t flip = 0u - h;
+        // structure = all_struct & !string_mask (avx/stage1.rs:400-406)
+        uint32_t m0 = s0 & ~(x0 ^ flip);
+        uint32_t m1 = s1 & ~(x1 ^ flip);
+        const uint32_t rel0 = tid * kBytesPerThread;
+        while (m0) {
+            sm.stage[slot++] = (uint16_t)(rel0 + (uint32_t)__ffs((int)m0) - 1u);
+            m0 &= m0 - 1u;  // blsr (stage1.rs:239)
+        }
+        while (m1) {
+            sm.stage[slot++] = (uint16_t)(rel0 + 32u + (uint32_t)__ffs((int)m1) - 1u);
+            m1 &= m1 - 1u;
+        }
+    }
+    __syncthreads();
+    {
+        const uint64_t tile_pos = p.pos_bias + tile_off;
+        if (head && tid == 0 && cnt > 0 && g0 < p.cap) p.index[g0] = tile_pos + sm.stage[1];
+        // staging index j = i + head is even for every pair
+        const uint32_t end = cnt + head;
+        for (uint32_t j = 2u * head + 2u * tid; j < end; j += 2u * kThreads) {
+            const uint64_t g = g0 + (j - head);
+            const uint32_t pr = *reinterpret_cast<const uint32_t*>(&sm.stage[j]);
+            const uint64_t e0 = tile_pos + (pr & 0xffffu);
+            if (j + 1 < end && g + 1 < p.cap) {
+                stg_128(p.index + g, e0, tile_pos + (pr >> 16));
+            } else if (g < p.cap) {
+                p.index[g] = e0;
+            }
+        }
+    }
+}
+
+// ---- pass A of the multi-GPU protocol: quote parity of a byte range ----------
+// Only the 1-bit parity has to be known before a shard can be indexed (the
+// counts fall out of the build itself), so this pass is a pure streaming
+// XOR-reduction: SWAR "byte == 0x22" flags are XOR-accumulated and popcounted once.
+__global__ void __launch_bounds__(256) quote_parity_kernel(const uint8_t* __restrict__ in, uint64_t n,
+                                                           uint32_t* __restrict__ out)
+{
+    const uint64_t nvec = n / 16;
+    uint32_t acc = 0u;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const uint4 v = ldg_stream_128(in + 16 * i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t x = w[k] ^ 0x22222222u;
+            // exact zero-byte test: bit 7 of every byte that equals zero
+            acc ^= ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+        }
+    }
+    uint32_t par = __popc(acc) & 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (uint64_t b = nvec * 16; b < n; ++b) par ^= (in[b] == 0x22) ? 1u : 0u;
+    }
+    par = __reduce_xor_sync(0xffffffffu, par);
+    __shared__ uint32_t s_par[8];
+    if ((threadIdx.x & 31) == 0) s_par[threadIdx.x >> 5] = par;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t ^= s_par[w];
+        if (t) atomicXor(out, 1u);
+    }
+}
+
+// ---- K1 known-answer exports --------------------------------------------------
+// quote_bits / all_struct words per 64-byte block, as get_struct_positions(16|3)
+// returns them (avx/stage1.rs:392,394); bytes past n read as zero.
+__global__ void block_masks_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ qw,
+                                   uint64_t* __restrict__ sw)
+{
+    const uint64_t nblocks = (n + 63) / 64;
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        uint32_t v = 0;
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t off = b * 64 + 4 * i + k;
+            if (off < n) v |= (uint32_t)in[off] << (8 * k);
+        }
+        w[i] = v;
+    }
+    const Masks32 m0 = classify32(w), m1 = classify32(w + 8);
+    qw[b] = (uint64_t)m0.quote | ((uint64_t)m1.quote << 32);
+    sw[b] = (uint64_t)m0.sep | ((uint64_t)m1.sep << 32);
+}
+
+// class byte per input byte: the deprecated structure::run (src/structure.rs:10-58)
+__global__ void class_bytes_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = class_byte(in[i]);
+}
+
+}  // namespace
+
+cudaError_t launch_index_build(const BuildParams& p, cudaStream_t stream)
+{
+    if (p.num_tiles == 0) return cudaSuccess;
+    index_build_kernel<<<p.num_tiles, kThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_quote_parity(const uint8_t* in, uint64_t n, uint32_t* out, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t blocks = (n / 16 + 255) / 256;
+    const uint64_t max_blocks = (uint64_t)sms * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks == 0) blocks = 1;
+    quote_parity_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_block_masks(const uint8_t* in, uint64_t n, uint64_t* qw, uint64_t* sw, cudaStream_t stream)
+{
+    const uint64_t nblocks = (n + 63) / 64;
+    if (nblocks == 0) return cudaSuccess;
+    block_masks_kernel<<<(unsigned)((nblocks + 127) / 128), 128, 0, stream>>>(in, n, qw, sw);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_class_bytes(const uint8_t* in, uint64_t n, uint8_t* out, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    class_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace csvb200

@@ -1,0 +1,72 @@
+// internal.h -- declarations shared by the CUDA translation units of libcsvb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace csvb200 {
+
+// ---- tile geometry of the fused index-build kernel --------------------------
+constexpr int kThreads = 256;                              // threads per CTA
+constexpr int kBytesPerThread = 64;                        // two 32-byte bit-slice groups
+constexpr int kTileBytes = kThreads * kBytesPerThread;     // 16 KiB of CSV per tile
+constexpr int kWarps = kThreads / 32;
+
+// ---- look-back descriptor (one u64 per tile, written/read as a single word) --
+//   [63:62] status   0 = not ready, 1 = tile aggregate, 2 = inclusive prefix
+//   [61]    parity   aggregate: quote parity of the tile; prefix: absolute parity at tile end
+//   aggregate: [19:0] c0 = unquoted separators if the tile is entered outside quotes
+//              [39:20] c1 = same if entered inside quotes
+//   prefix:    [60:0] absolute number of index entries emitted up to the tile end
+constexpr uint64_t kStatusAgg = 1ull << 62;
+constexpr uint64_t kStatusPrefix = 2ull << 62;
+constexpr uint64_t kParityBit = 1ull << 61;
+constexpr uint64_t kCountMask = (1ull << 61) - 1;
+
+struct BuildParams {
+    const uint8_t* in;       // 16-byte aligned device pointer to the shard's bytes
+    uint64_t n;              // bytes
+    uint64_t* index;         // output entries (u64, == Rust usize); 16-byte aligned
+    uint64_t cap;            // number of u64 slots available at `index`
+    uint64_t out_base;       // slot of the first entry produced by the virtual predecessor (1 after the sentinel)
+    uint64_t pos_bias;       // added to every emitted byte position (global offset of the shard)
+    const uint64_t* carry;   // optional device cell {entries so far, parity}; overrides the two below
+    uint64_t carry_count;    // entries emitted by earlier launches of the same build
+    uint32_t carry_parity;   // quote parity entering byte 0 of `in`
+    uint32_t num_tiles;
+    uint64_t* desc;          // [num_tiles] look-back descriptors, zeroed before launch
+    uint32_t* ticket;        // dynamic tile counter, zeroed before launch
+    uint64_t* result;        // {entries emitted through the end of this launch, end parity}
+};
+
+cudaError_t launch_index_build(const BuildParams& p, cudaStream_t stream);
+
+// quote parity of a byte range (pass A of the multi-GPU protocol); *out ^= parity
+cudaError_t launch_quote_parity(const uint8_t* in, uint64_t n, uint32_t* out, cudaStream_t stream);
+
+// debug / known-answer exports (K1): per 64-byte block quote and separator words, class bytes
+cudaError_t launch_block_masks(const uint8_t* in, uint64_t n, uint64_t* quote_words, uint64_t* sep_words,
+                               cudaStream_t stream);
+cudaError_t launch_class_bytes(const uint8_t* in, uint64_t n, uint8_t* out, cudaStream_t stream);
+
+// K4 batched lookups. ranges[2*i] = start, ranges[2*i+1] = end; (UINT64_MAX, UINT64_MAX) = None.
+struct LookupParams {
+    const uint64_t* index;
+    uint64_t index_len;
+    uint32_t record_cnt;
+    uint32_t field_cnt;
+    uint32_t row_size;       // jump: field_cnt (+1 for CRLF)
+    const uint32_t* rec;
+    const uint32_t* fld;     // nullptr => seek_record
+    uint64_t nq;
+    uint64_t* ranges;
+    uint32_t* oob;           // incremented for queries whose index slot is out of bounds (reference would panic)
+};
+cudaError_t launch_seek(const LookupParams& p, cudaStream_t stream);
+
+// gather the bytes of resolved ranges into a packed buffer: out[out_off[i] .. out_off[i+1]) = bytes[start..end)
+cudaError_t launch_gather_bytes(const uint8_t* bytes, const uint64_t* ranges, const uint64_t* out_off, uint64_t nq,
+                                uint8_t* out, cudaStream_t stream);
+cudaError_t launch_range_lengths(const uint64_t* ranges, uint64_t nq, uint64_t* lens, cudaStream_t stream);
+
+}  // namespace csvb200

@@ -1,0 +1,153 @@
+/*
+ * csvb200.h -- C ABI of libcsvb200: the B200 (sm_100a) drop-in for csv-simd's hot path
+ *
+ *     csv bytes -> in-memory structural index -> (record #) -> record -> (record, field #) -> field
+ *
+ * The reference (EdmundsEcho/csv-simd, a Rust crate) has no FFI; the boundary is its
+ * public Rust API.  Every entry point below names the reference item it replaces
+ * (file:line under the reference tree).  INTEGRATION.md shows the `extern "C"` block
+ * and the replacement bodies of reader.rs / record_source.rs that bind these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns a csvb200_status (0 = OK)
+ *     and never unwinds across the ABI; csvb200_last_error(ctx) gives the detail string.
+ *   - one csvb200_ctx per GPU and per host thread at a time (process-per-GPU model);
+ *     built indexes are immutable and may be queried concurrently.
+ *   - the index is an array of native-endian u64 byte offsets, ABI-identical to the
+ *     reference's StructureIndex(Vec<CodeUnitPos>) (src/stage1.rs:61,67):
+ *       index[0] = 0 (sentinel, src/reader.rs:216), then every ',', CR or LF byte that
+ *       lies outside double-quoted regions, in file order; CR and LF are separate entries.
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef CSVB200_H
+#define CSVB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSVB200_VERSION 100 /* 0.1.0 */
+
+typedef enum csvb200_status {
+    CSVB200_OK = 0,
+    CSVB200_ERR_INVALID_ARG = 1,
+    CSVB200_ERR_INVALID_STATE = 2,      /* StructureError::InvalidState      (src/error.rs:17-18) */
+    CSVB200_ERR_INVALID_CSV_FORMAT = 3, /* StructureError::InvalidCsvFormat  (src/error.rs:19-20) */
+    CSVB200_ERR_MISSING_VALUE = 4,      /* StructureError::MissingValue      (src/error.rs:15-16) */
+    CSVB200_ERR_IO = 5,                 /* StructureError::Io                (src/error.rs:11-12) */
+    CSVB200_ERR_CUDA = 6,
+    CSVB200_ERR_OOM = 7,
+    CSVB200_ERR_INPUT_TOO_SMALL = 8,    /* n < 64: the reference panics (src/reader.rs:220-229, src/avx/stage1.rs:45-48) */
+    CSVB200_ERR_CAPACITY = 9,
+    CSVB200_ERR_OUT_OF_BOUNDS = 10      /* a lookup slot past the index end: the reference panics on the Vec bounds check */
+} csvb200_status;
+
+typedef struct csvb200_ctx csvb200_ctx;
+typedef struct csvb200_index csvb200_index;
+
+/* (start, end) byte range of a record or field in the input; both UINT64_MAX = None. */
+typedef struct csvb200_range {
+    uint64_t start;
+    uint64_t end;
+} csvb200_range;
+
+/* build flags */
+#define CSVB200_BUILD_DEFAULT 0u
+#define CSVB200_BUILD_KEEP_BYTES 1u   /* keep the device copy of the input for csvb200_gather_fields */
+#define CSVB200_BUILD_STRICT_MIN64 2u /* mirror the reference's n < 64 panic as CSVB200_ERR_INPUT_TOO_SMALL */
+
+int csvb200_version(void);
+const char* csvb200_status_string(int status);
+
+/* ---- context ----------------------------------------------------------------------------- */
+/* Creates the per-GPU context: stream, look-back scratch, pinned result cells.  `device` is a
+ * CUDA ordinal.  Fails with CSVB200_ERR_CUDA when no usable device exists (no CPU fallback). */
+int csvb200_ctx_create(int device, csvb200_ctx** out);
+void csvb200_ctx_destroy(csvb200_ctx* ctx);
+const char* csvb200_last_error(const csvb200_ctx* ctx);
+/* Run all work of this context on an externally owned cudaStream_t (e.g. the caller's current
+ * stream, so the caller's CUDA events bracket the kernels).  NULL restores the private stream. */
+int csvb200_ctx_set_stream(csvb200_ctx* ctx, void* cuda_stream);
+/* Initial index capacity = n / ratio_den * ratio_num + 4096 entries (default 1/3); an index that
+ * overflows it is transparently rebuilt with the exact size. */
+int csvb200_ctx_set_reserve(csvb200_ctx* ctx, uint32_t ratio_num, uint32_t ratio_den);
+/* Device time (ms, CUDA events on the context's stream) of the kernels of the last build call. */
+int csvb200_ctx_last_build_ms(csvb200_ctx* ctx, float* ms);
+/* Number of kernel launches issued by this context so far. */
+uint64_t csvb200_ctx_launch_count(const csvb200_ctx* ctx);
+
+/* pinned host memory for staging (cudaHostAlloc / cudaFreeHost) */
+int csvb200_host_alloc(size_t bytes, void** out);
+int csvb200_host_free(void* p);
+
+/* ---- csv -> index : replaces reader::read (src/reader.rs:150-306) -------------------------- */
+/* Host bytes -> device-resident index.  Copies the input to the GPU in chunks
+ * (cudaMemcpyAsync from pinned memory; pageable input is staged through a pinned ring),
+ * runs the fused classify / quote-scan / compaction kernel, leaves the index in HBM. */
+int csvb200_index_build(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint32_t flags,
+                        csvb200_index** out);
+/* Same, input already in device memory (16-byte aligned).  Asynchronous: returns after
+ * enqueueing; csvb200_index_len / copy_out / sync wait for completion. */
+int csvb200_index_build_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t flags,
+                               csvb200_index** out);
+/* Host bytes -> host index in one call, H2D and D2H overlapped chunk by chunk (the end-to-end
+ * path the reference's callers see: &[u8] in, Vec<usize> out).  dst_cap in entries; *len_out
+ * receives the entry count; CSVB200_ERR_CAPACITY (with *len_out set) if dst is too small. */
+int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst,
+                                size_t dst_cap, size_t* len_out);
+
+/* ---- sharded build (multi-GPU, SURVEY 8e / README.md:24 "splitting work without first knowing
+ * record breaks") --------------------------------------------------------------------------- */
+/* Pass A: quote parity (0/1) of a device-resident shard -- the only thing that must cross GPUs
+ * before a shard can be indexed. */
+int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t* parity_out);
+/* Pass B: index a shard that is entered with quote parity `carry_parity` and starts at global
+ * byte offset `global_offset`; the sentinel entry is emitted only when emit_sentinel != 0
+ * (rank 0).  Positions are global. */
+int csvb200_index_build_shard_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity,
+                                     uint64_t global_offset, int emit_sentinel, csvb200_index** out);
+
+/* ---- index object: StructureIndex (src/stage1.rs:61) --------------------------------------- */
+int csvb200_index_sync(csvb200_index* idx);
+size_t csvb200_index_len(csvb200_index* idx);          /* entries incl. the sentinel if emitted */
+int csvb200_index_end_parity(csvb200_index* idx);      /* quote parity after the last byte */
+const uint64_t* csvb200_index_device_ptr(csvb200_index* idx);
+int csvb200_index_copy_out(csvb200_index* idx, uint64_t* dst, size_t dst_cap); /* fills a caller Vec<usize> */
+void csvb200_index_free(csvb200_index* idx);
+
+/* ---- Tape metadata: TapeCore::init (src/tape.rs:315-347) ----------------------------------- */
+/* jump = field_cnt (+1 for CRLF); record_cnt = (len-1)/jump; (len-1)%jump != 0 ->
+ * CSVB200_ERR_INVALID_CSV_FORMAT.  Must precede the seek calls (else CSVB200_ERR_INVALID_STATE,
+ * as TapeCore::record_jump_size, src/tape.rs:200-201). */
+int csvb200_tape_init(csvb200_index* idx, uint32_t field_cnt, int crlf, uint32_t* record_cnt, uint64_t* jump);
+
+/* ---- lookups: RecordSource (src/record_source.rs:70-140) ----------------------------------- */
+/* scalar: *found = 0 means Ok(None) */
+int csvb200_seek_record(csvb200_index* idx, uint32_t record_idx, csvb200_range* out, int* found);
+int csvb200_seek_field(csvb200_index* idx, uint32_t record_idx, uint32_t field_idx, csvb200_range* out, int* found);
+/* batched (K4), host arrays in / out */
+int csvb200_seek_records(csvb200_index* idx, const uint32_t* rec, size_t nq, csvb200_range* out);
+int csvb200_seek_fields(csvb200_index* idx, const uint32_t* rec, const uint32_t* fld, size_t nq, csvb200_range* out);
+/* batched, device arrays in / out, asynchronous on the context's stream */
+int csvb200_seek_fields_device(csvb200_index* idx, const uint32_t* d_rec, const uint32_t* d_fld, size_t nq,
+                               csvb200_range* d_out);
+int csvb200_seek_records_device(csvb200_index* idx, const uint32_t* d_rec, size_t nq, csvb200_range* d_out);
+/* materialise the field bytes of a batch (needs CSVB200_BUILD_KEEP_BYTES): out_offsets[nq+1] are
+ * exclusive prefix sums of the lengths, out receives the packed bytes (out_cap bytes). */
+int csvb200_gather_fields(csvb200_index* idx, const uint32_t* rec, const uint32_t* fld, size_t nq,
+                          uint64_t* out_offsets, uint8_t* out, size_t out_cap);
+
+/* ---- K1 known-answer exports (debug) -------------------------------------------------------- */
+/* per 64-byte block: quote_bits / all_struct as get_struct_positions(16 | 3) (src/avx/stage1.rs:392,394) */
+int csvb200_block_masks(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* quote_words,
+                        uint64_t* sep_words);
+/* class byte per input byte: structure::run (src/structure.rs:10-58) */
+int csvb200_class_bytes(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSVB200_H */

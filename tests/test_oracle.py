@@ -1,0 +1,136 @@
+"""CPU tests of the oracle itself: pins it against everything the reference's own tests hold
+for this path, against the committed golden vectors, and against an independent closed form."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import cases
+from tests.conftest import golden_bytes
+
+
+def test_reference_mk_index_pin():
+    # src/reader.rs:318-327: index[1] == 4, index[last] == 95 on res/reader_test01.csv
+    idx = O.read_sse(golden_bytes("reader_test01.csv"))
+    assert idx[1] == 4
+    assert idx[-1] == 95
+
+
+def test_reference_blsr_identity():
+    # src/lib.rs:139-152: 0b01011100 & (0b01011100 - 1) == 0b01011000
+    assert O.blsr(0b01011100) == 0b01011000
+    assert O.blsr(0) == 0
+
+
+def test_reference_boundaries_doctest():
+    # src/tape.rs:362-384
+    r = O.boundaries(8, 3)
+    assert r == [(0, 3), (3, 3), (6, 2)] and sum(l for _, l in r) == 8
+    r = O.boundaries(1000, 12)
+    assert r[0] == (0, 84) and r[1] == (84, 84) and r[11] == (917, 83)
+    assert sum(l for _, l in r) == 1000
+    assert O.boundaries(8, 12) == [(0, 8)]
+    assert O.boundaries(0, 3) is None
+
+
+@pytest.mark.parametrize("name", ["reader_test01.csv", "sample.csv", "sample_rx.csv"])
+def test_golden_vectors(golden, name):
+    data = golden_bytes(name)
+    g = golden[name]
+    assert len(data) == g["n"]
+    idx = O.read_sse(data)
+    assert idx.tolist() == g["index"]
+    assert O.read_closed_form(data)[0].tolist() == g["index"]
+    assert O.closed_form_numpy(data).tolist() == g["index"]
+    h = O.header_new(data)
+    assert (h.header, h.crlf, h.field_cnt, h.record_offset) == (g["header"], g["crlf"], g["field_cnt"],
+                                                                g["record_offset"])
+    if g["tape_ok"]:
+        assert O.tape_init(len(idx), h.field_cnt, h.crlf) == (g["jump"], g["record_cnt"])
+    else:
+        with pytest.raises(O.InvalidCsvFormat):
+            O.tape_init(len(idx), h.field_cnt, h.crlf)
+
+
+@pytest.mark.parametrize("name", ["sample.csv", "sample_rx.csv"])
+def test_golden_seeks(golden, name):
+    data = golden_bytes(name)
+    g = golden[name]
+    idx = np.asarray(g["index"], dtype=np.uint64)
+    for r, want in g["seek_record"].items():
+        rg = O.seek_record(idx, len(data), g["record_cnt"], g["jump"], g["field_cnt"], int(r))
+        got = None if rg is None else data[rg[0]:rg[1]].decode()
+        assert got == want
+    for key, want in g["seek_field"].items():
+        r, f = map(int, key.split(","))
+        rg = O.seek_field(idx, len(data), g["record_cnt"], g["field_cnt"], g["crlf"], r, f)
+        got = None if rg is None else data[rg[0]:rg[1]].decode()
+        assert got == want
+
+
+def test_survey_known_answers(golden):
+    # values derived independently during the survey
+    g = golden["sample.csv"]
+    assert len(g["index"]) == 46 and g["record_cnt"] == 15 and g["jump"] == 3
+    assert g["seek_record"]["0"] == 'Edm nd,3, "o"' and g["seek_field"]["6,0"] == "iharlotte"
+    g = golden["sample_rx.csv"]
+    assert len(g["index"]) == 73 and g["record_cnt"] == 8 and g["jump"] == 9 and g["record_offset"] == 128
+    assert g["seek_field"]["1,2"] == '"INTERNAL MED, CARD. ELECTROPHYSIOLOGY"'
+    assert golden["reader_test01.csv"]["tape_ok"] is False and len(golden["reader_test01.csv"]["index"]) == 17
+
+
+@pytest.mark.parametrize("name,data", cases.edge_cases(), ids=[c[0] for c in cases.edge_cases()])
+def test_sse_restatement_equals_closed_form(name, data):
+    a = O.read_sse(data)
+    b, _ = O.read_closed_form(data)
+    assert a.shape == b.shape and (a == b).all()
+    assert (O.closed_form_numpy(data) == b).all()
+
+
+def test_fuzz_sse_vs_closed_form():
+    for seed in range(300):
+        n = 64 + (seed * 37) % 700
+        data = cases.rand_bytes(n, seed) if seed % 3 else cases.full_random(n, seed)
+        a = O.read_sse(data)
+        b, _ = O.read_closed_form(data)
+        assert (a == b).all(), seed
+
+
+def test_small_inputs_panic_in_reference():
+    for _, data in cases.small_cases():
+        with pytest.raises(O.OraclePanic):
+            O.read_sse(data)
+
+
+def test_class_bytes_all_256():
+    # LUT enumeration (src/stage1.rs:24-35): only six byte values classify
+    data = bytes(range(256))
+    got = np.concatenate([O.structure_run(data, at) for at in range(0, 256, 16)])
+    want = np.zeros(256, dtype=np.uint8)
+    want[0x0A] = want[0x0D] = 1
+    want[0x2C] = 2
+    want[0x20] = 4
+    want[0x5C] = 8
+    want[0x22] = 16
+    assert (got == want).all()
+
+
+def test_shard_summary_composes():
+    data = cases.rand_bytes(5000, 11)
+    full, _ = O.read_closed_form(data)
+    cuts = [0, 13, 1700, 1701, 3333, 5000]
+    par, segs = 0, []
+    for k in range(len(cuts) - 1):
+        seg = data[cuts[k]:cuts[k + 1]]
+        p, c0, s = O.shard_summary(seg)
+        idx, endp = O.read_closed_form(seg, start_parity=par, pos_bias=cuts[k], with_sentinel=(k == 0))
+        assert len(idx) - (1 if k == 0 else 0) == (s - c0 if par else c0)
+        assert endp == par ^ p
+        segs.append(idx)
+        par ^= p
+    assert (np.concatenate(segs) == full).all()
+
+
+def test_chunks_restatement():
+    ch = O.chunks(15, 3, 4)
+    assert [c["record_cnt"] for c in ch] == [3, 4, 4, 3] and ch[0]["start"] == 3 and ch[-1]["end"] == 45
+    assert O.chunks(0, 3, 4) is None
