@@ -42,6 +42,9 @@ SIGNATURES = {
     "csvb200_shard_quote_parity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u32p]),
     "csvb200_index_build_shard_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64,
                                                    C.c_int, vpp]),
+    "csvb200_shard_quote_parity_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_index_build_shard_device_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32,
+                                                      C.c_uint64, C.c_int, C.c_void_p, vpp]),
     "csvb200_index_sync": (C.c_int, [C.c_void_p]),
     "csvb200_index_len": (C.c_size_t, [C.c_void_p]),
     "csvb200_index_end_parity": (C.c_int, [C.c_void_p]),

@@ -110,6 +110,19 @@ class Context:
                                                                global_offset, int(emit_sentinel), C.byref(h)))
         return StructureIndex(self, h)
 
+    def shard_quote_parity_device(self, dev_ptr: int, n: int, d_parity_out: int):
+        self._check(self._lib.csvb200_shard_quote_parity_device(self._h, C.c_void_p(dev_ptr), n,
+                                                                C.c_void_p(d_parity_out)))
+
+    def index_build_shard_device_ex(self, dev_ptr: int, n: int, d_shard_parities: int, shard_rank: int,
+                                    global_offset: int, emit_sentinel: bool, d_result_out: int = 0
+                                    ) -> "StructureIndex":
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_build_shard_device_ex(
+            self._h, C.c_void_p(dev_ptr), n, C.c_void_p(d_shard_parities), shard_rank, global_offset,
+            int(emit_sentinel), C.c_void_p(d_result_out or 0), C.byref(h)))
+        return StructureIndex(self, h)
+
     # -- K1 known-answer exports ------------------------------------------------------------
     def block_masks(self, data):
         a = _as_u8(data)

@@ -58,6 +58,9 @@ struct csvb200_index {
     uint32_t carry_parity = 0;
     uint64_t pos_bias = 0;
     uint64_t out_base = 1;
+    const uint32_t* d_shard_par = nullptr;  // device-resident shard parities (multi-GPU), or null
+    uint32_t shard_rank = 0;
+    uint64_t* d_result2 = nullptr;          // optional caller-owned device copy of {count, parity}
     uint8_t* d_bytes_owned = nullptr;
     // Tape metadata (TapeCore::init)
     bool tape_ready = false;
@@ -107,7 +110,9 @@ int enqueue_build(csvb200_index* idx, bool timed)
 {
     csvb200_ctx* ctx = idx->ctx;
     const size_t n = idx->n;
-    const uint64_t num_tiles = (n + kTileBytes - 1) / kTileBytes;
+    uint64_t num_tiles = (n + kTileBytes - 1) / kTileBytes;
+    // an empty shard still runs one (empty) tile when its carry / result live on the device
+    if (num_tiles == 0 && (idx->d_shard_par || idx->d_result2)) num_tiles = 1;
     if (num_tiles > 0xffffffffull) return fail(ctx, CSVB200_ERR_INVALID_ARG, "input too large for one launch");
     uint64_t* d_cell = ctx->d_cells + idx->cell * kCellWords;
     uint64_t* h_cell = ctx->h_cells + idx->cell * kCellWords;
@@ -134,6 +139,9 @@ int enqueue_build(csvb200_index* idx, bool timed)
         p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
         p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 16);
         p.result = d_cell;
+        p.result2 = idx->d_result2;
+        p.shard_par = idx->d_shard_par;
+        p.shard_rank = idx->shard_rank;
         if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
         CU_TRY(ctx, launch_index_build(p, ctx->stream));
         ctx->launches += 1;
@@ -165,7 +173,8 @@ int new_index(csvb200_ctx* ctx, csvb200_index** out)
 }
 
 int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity, uint64_t pos_bias,
-                        int emit_sentinel, csvb200_index** out)
+                        int emit_sentinel, csvb200_index** out, const uint32_t* d_shard_par = nullptr,
+                        uint32_t shard_rank = 0, uint64_t* d_result2 = nullptr)
 {
     if (!ctx || !out || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     if ((reinterpret_cast<uintptr_t>(dev_bytes) & 15u) != 0)
@@ -179,6 +188,9 @@ int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint3
     idx->carry_parity = carry_parity & 1u;
     idx->pos_bias = pos_bias;
     idx->out_base = emit_sentinel ? 1 : 0;
+    idx->d_shard_par = d_shard_par;
+    idx->shard_rank = shard_rank;
+    idx->d_result2 = d_result2;
     idx->cap = initial_cap(ctx, n);
     cudaError_t e = cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream);
     if (e != cudaSuccess) {
@@ -369,6 +381,27 @@ int csvb200_index_build_shard_device(csvb200_ctx* ctx, const void* dev_bytes, si
                                      uint64_t global_offset, int emit_sentinel, csvb200_index** out)
 {
     return build_device_common(ctx, dev_bytes, n, carry_parity, global_offset, emit_sentinel, out);
+}
+
+int csvb200_index_build_shard_device_ex(csvb200_ctx* ctx, const void* dev_bytes, size_t n,
+                                        const uint32_t* d_shard_parities, uint32_t shard_rank, uint64_t global_offset,
+                                        int emit_sentinel, uint64_t* d_result_out, csvb200_index** out)
+{
+    if (ctx && !d_shard_parities) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null shard parity array");
+    return build_device_common(ctx, dev_bytes, n, 0u, global_offset, emit_sentinel, out, d_shard_parities, shard_rank,
+                               d_result_out);
+}
+
+int csvb200_shard_quote_parity_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t* d_parity_out)
+{
+    if (!ctx || !d_parity_out || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    if ((reinterpret_cast<uintptr_t>(dev_bytes) & 15u) != 0)
+        return fail(ctx, CSVB200_ERR_INVALID_ARG, "device input must be 16-byte aligned");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemsetAsync(d_parity_out, 0, sizeof(uint32_t), ctx->stream));
+    CU_TRY(ctx, launch_quote_parity(static_cast<const uint8_t*>(dev_bytes), n, d_parity_out, ctx->stream));
+    if (n) ctx->launches += 1;
+    return CSVB200_OK;
 }
 
 int csvb200_index_build(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint32_t flags, csvb200_index** out)

@@ -187,14 +187,21 @@ __global__ void __launch_bounds__(kThreads, 4) index_build_kernel(const BuildPar
         if (lane == 0)
             st_relaxed_u64(p.desc + tile, kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
 
-        // virtual predecessor of tile 0: the carry entering this launch
-        uint64_t carry_count = p.carry_count;
-        uint32_t carry_parity = p.carry_parity;
-        if (p.carry != nullptr) {
-            carry_count = p.carry[0];
-            carry_parity = (uint32_t)p.carry[1] & 1u;
-        }
-        const uint64_t virt = kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
+        // virtual predecessor of tile 0: the carry entering this launch (only tiles whose look-back
+        // window reaches below tile 0 ever evaluate it)
+        auto virtual_prefix = [&]() -> uint64_t {
+            uint64_t carry_count = p.carry_count;
+            uint32_t carry_parity = p.carry_parity;
+            if (p.carry != nullptr) {
+                carry_count = p.carry[0];
+                carry_parity = (uint32_t)p.carry[1] & 1u;
+            }
+            if (p.shard_par != nullptr) {
+                carry_parity = 0u;
+                for (uint32_t j = 0; j < p.shard_rank; ++j) carry_parity ^= p.shard_par[j] & 1u;
+            }
+            return kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
+        };
 
         // suffix composite S of the tiles already absorbed (those nearest to us)
         uint32_t sp = 0u;
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 4) index_build_kernel(const BuildPar
         uint32_t pin;
         uint64_t base;
         while (true) {
-            const uint64_t d = idx >= 0 ? ld_relaxed_u64(p.desc + idx) : virt;
+            const uint64_t d = idx >= 0 ? ld_relaxed_u64(p.desc + idx) : virtual_prefix();
             const uint32_t status = (uint32_t)(d >> 62);
             const uint32_t pref = __ballot_sync(0xffffffffu, status == 2u);
             const uint32_t inval = __ballot_sync(0xffffffffu, status == 0u);
@@ -247,6 +254,10 @@ __global__ void __launch_bounds__(kThreads, 4) index_build_kernel(const BuildPar
             if (tile == p.num_tiles - 1) {
                 p.result[0] = cend;
                 p.result[1] = pend;
+                if (p.result2 != nullptr) {
+                    p.result2[0] = cend;
+                    p.result2[1] = pend;
+                }
             }
         }
     }

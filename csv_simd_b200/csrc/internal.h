@@ -37,6 +37,11 @@ struct BuildParams {
     uint64_t* desc;          // [num_tiles] look-back descriptors, zeroed before launch
     uint32_t* ticket;        // dynamic tile counter, zeroed before launch
     uint64_t* result;        // {entries emitted through the end of this launch, end parity}
+    uint64_t* result2;       // optional second copy of `result` in caller-owned device memory
+    // multi-GPU: quote parities of all shards as all-gathered on the device; the carry-in parity of
+    // this shard is the XOR of shard_par[0 .. shard_rank) (overrides carry_parity when non-null)
+    const uint32_t* shard_par;
+    uint32_t shard_rank;
 };
 
 cudaError_t launch_index_build(const BuildParams& p, cudaStream_t stream);

@@ -71,13 +71,36 @@ class ShardedIndex:
     parities: List[int]
 
 
-def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: int, group=None) -> ShardedIndex:
+def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: int, group=None,
+                        resolve: bool = True) -> ShardedIndex:
     """Index this rank's shard [global_offset, global_offset + n) of a file split across the ranks
-    of `group` at arbitrary byte offsets."""
+    of `group` at arbitrary byte offsets.
+
+    Everything between pass A and the end of pass B is stream-ordered on the current CUDA stream
+    (which the Context must be bound to, see Context.set_stream): parity kernel -> NCCL all_gather
+    of 4 bytes per rank -> build kernel that XORs the gathered parities of the lower ranks on the
+    device -> NCCL all_gather of the entry counts.  The host only synchronises once, at the end,
+    to learn the segment length (resolve=False skips even that; fields base/total_len/carry_in are
+    then -1 and `counts` holds the device tensor)."""
     rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
     device = torch.device("cuda", ctx.device)
-    p = ctx.shard_quote_parity(dev_ptr, n)                       # pass A
-    carry, ps = exchange_parity(p, group, device)                # 8 bytes per rank over NVLink
-    idx = ctx.index_build_shard_device(dev_ptr, n, carry, global_offset, emit_sentinel=(rank == 0))  # pass B
-    base, total = exchange_counts(len(idx), group, device)
-    return ShardedIndex(idx, base, total, carry, ps)
+    par_local = torch.empty(1, dtype=torch.int32, device=device)
+    ctx.shard_quote_parity_device(dev_ptr, n, par_local.data_ptr())              # pass A
+    pars = torch.empty(world, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(pars, par_local, group=group)                   # 4 bytes per rank over NVLink
+    res_local = torch.empty(2, dtype=torch.int64, device=device)
+    idx = ctx.index_build_shard_device_ex(dev_ptr, n, pars.data_ptr(), rank, global_offset,
+                                          emit_sentinel=(rank == 0), d_result_out=res_local.data_ptr())  # pass B
+    res_all = torch.empty(2 * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(res_all, res_local, group=group)                # entry counts / end parities
+    idx._keepalive = (par_local, pars, res_local, res_all)
+    if not resolve:
+        out = ShardedIndex(idx, -1, -1, -1, [])
+        out.counts = res_all
+        return out
+    host = res_all.cpu().tolist()                                               # the only host sync
+    counts = [int(c) for c in host[0::2]]
+    counts[0] += 1                                                              # sentinel lives on rank 0
+    ps = [int(v) for v in pars.cpu().tolist()]
+    return ShardedIndex(idx, exclusive_bases(counts)[rank], sum(counts), carry_in_parities(ps)[rank], ps)

@@ -110,6 +110,17 @@ int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n
 int csvb200_index_build_shard_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity,
                                      uint64_t global_offset, int emit_sentinel, csvb200_index** out);
 
+/* Stream-ordered forms of the two passes: no host synchronisation between pass A, the collective and
+ * pass B.  Pass A writes the parity to a device cell; after the caller has all-gathered the cells
+ * into d_shard_parities[world] (NCCL, same stream order), pass B derives its carry-in parity on the
+ * device as XOR of d_shard_parities[0 .. shard_rank).  d_result_out (optional, 2 x u64 device words)
+ * receives {entries emitted by this shard excluding the sentinel, end parity} for a device-side
+ * all-gather of the counts. */
+int csvb200_shard_quote_parity_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t* d_parity_out);
+int csvb200_index_build_shard_device_ex(csvb200_ctx* ctx, const void* dev_bytes, size_t n,
+                                        const uint32_t* d_shard_parities, uint32_t shard_rank, uint64_t global_offset,
+                                        int emit_sentinel, uint64_t* d_result_out, csvb200_index** out);
+
 /* ---- index object: StructureIndex (src/stage1.rs:61) --------------------------------------- */
 int csvb200_index_sync(csvb200_index* idx);
 size_t csvb200_index_len(csvb200_index* idx);          /* entries incl. the sentinel if emitted */

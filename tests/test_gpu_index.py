@@ -1,0 +1,307 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs (bit-exact: the index is integer data), the committed golden vectors, and -- at
+BASELINE.json's full sizes -- size-independent properties."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import csv_simd_b200 as cs
+from oracle import oracle as O
+from tests import cases
+from tests.conftest import golden_bytes
+from tools import gen
+
+pytestmark = pytest.mark.gpu
+
+U64MAX = 0xFFFFFFFFFFFFFFFF
+
+
+def build(ctx, data, flags=0):
+    idx = ctx.index_build(data, flags)
+    out = idx.to_host().copy()
+    par = idx.end_parity
+    idx.free()
+    return out, par
+
+
+# ---- golden vectors (config 1: res/sample.csv -> stage1 -> tape index) -------------------------
+@pytest.mark.parametrize("name", ["reader_test01.csv", "sample.csv", "sample_rx.csv"])
+def test_golden_index(ctx, golden, name):
+    data = golden_bytes(name)
+    got, _ = build(ctx, data)
+    assert got.tolist() == golden[name]["index"]
+
+
+def test_reference_mk_index_pin(ctx):
+    got, _ = build(ctx, golden_bytes("reader_test01.csv"))  # src/reader.rs:318-327
+    assert got[1] == 4 and got[-1] == 95
+
+
+@pytest.mark.parametrize("name", ["sample.csv", "sample_rx.csv"])
+def test_golden_tape_and_seeks(ctx, golden, name):
+    g = golden[name]
+    with tempfile.NamedTemporaryFile(suffix=".csv", delete=False) as f:
+        f.write(golden_bytes(name))
+        path = f.name
+    try:
+        tape = cs.create(path, ctx)  # the reference's factory: open -> mmap -> Header -> read -> Tape
+        assert tape.header() == g["header"]
+        assert tape.record_cnt() == g["record_cnt"] and tape.record_jump_size() == g["jump"]
+        assert tape.index().to_host().tolist() == g["index"]
+        data = golden_bytes(name)
+        for r, want in g["seek_record"].items():
+            assert tape.seek_record(int(r)) == want
+            rg = tape.index().seek_record(int(r))  # device scalar path
+            assert (None if rg is None else data[rg[0]:rg[1]].decode()) == want
+        for key, want in g["seek_field"].items():
+            r, f = map(int, key.split(","))
+            assert tape.seek_field(r, f) == want
+            rg = tape.index().seek_field(r, f)
+            assert (None if rg is None else data[rg[0]:rg[1]].decode()) == want
+        # Display of WithRecordSource prints first / last record: last = record_cnt - 2
+        assert tape.seek_record(g["record_cnt"] - 2) is not None
+        assert tape.seek_record(g["record_cnt"] - 1) is None
+    finally:
+        os.unlink(path)
+
+
+def test_invalid_csv_format(ctx):
+    with tempfile.NamedTemporaryFile(suffix=".csv", delete=False) as f:
+        f.write(golden_bytes("reader_test01.csv"))  # ragged last row: (E-1) % jump != 0
+        path = f.name
+    try:
+        with pytest.raises(cs.InvalidCsvFormat):
+            cs.create(path, ctx)
+    finally:
+        os.unlink(path)
+
+
+def test_seek_before_init_is_invalid_state(ctx):
+    data = golden_bytes("sample.csv")
+    mm = cs.Mmap(data=data)
+    core = cs.TapeCore.create(mm, cs.reader.read(mm, ctx), cs.Header.new(mm))
+    with pytest.raises(cs.InvalidState):   # record_cnt() is None before init (record_source.rs:77-79)
+        core.seek_record(0)
+    with pytest.raises(cs.InvalidState):
+        core.index().seek_field(0, 0)      # C ABI: csvb200_tape_init not called yet
+    core.init()
+    assert core.seek_record(0) == 'Edm nd,3, "o"'
+
+
+# ---- edge semantics ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,data", cases.edge_cases(), ids=[c[0] for c in cases.edge_cases()])
+def test_edge_cases_vs_sse_oracle(ctx, name, data):
+    want = O.read_sse(data)  # literal restatement of the reference
+    got, par = build(ctx, data)
+    assert got.shape == want.shape and (got == want).all()
+    assert par == (data.count(b'"') & 1)
+
+
+@pytest.mark.parametrize("name,data", cases.small_cases(), ids=[c[0] for c in cases.small_cases()])
+def test_small_inputs(ctx, name, data):
+    # n < 64: the reference panics; the C ABI returns the closed form, or mirrors the panic on request
+    want, _ = O.read_closed_form(data)
+    got, _ = build(ctx, data)
+    assert (got == want).all()
+    with pytest.raises(cs.ReferencePanic):
+        ctx.index_build(data, cs.BUILD_STRICT_MIN64)
+    with pytest.raises(cs.ReferencePanic):
+        cs.reader.read(data, ctx)
+
+
+def test_fuzz_vs_oracle(ctx):
+    for seed in range(120):
+        n = 64 + (seed * 7919) % 70000
+        data = cases.full_random(n, seed) if seed % 4 == 0 else cases.rand_bytes(n, seed)
+        want = O.read_sse(data)
+        got, _ = build(ctx, data)
+        assert got.shape == want.shape and (got == want).all(), (seed, n)
+
+
+def test_capacity_overflow_rebuild(ctx):
+    # denser than the reserve heuristic (one entry per byte): transparently rebuilt with the exact size
+    data = b"," * (1 << 20)
+    ctx.set_reserve(1, 64)
+    try:
+        got, _ = build(ctx, data)
+    finally:
+        ctx.set_reserve(1, 3)
+    assert got.size == (1 << 20) + 1 and (got[1:] == np.arange(1 << 20, dtype=np.uint64)).all()
+
+
+# ---- K1 known-answer exports --------------------------------------------------------------------
+def test_block_masks_vs_closed_form(ctx):
+    data = np.frombuffer(cases.rand_bytes(100003, 5), dtype=np.uint8)
+    q, s = ctx.block_masks(data)
+    pad = np.zeros(q.size * 64, dtype=np.uint8)
+    pad[:data.size] = data
+    wq = np.packbits((pad == 0x22).reshape(-1, 64), axis=1, bitorder="little").view(np.uint64).ravel()
+    ws = np.packbits(((pad == 0x2C) | (pad == 0x0D) | (pad == 0x0A)).reshape(-1, 64), axis=1,
+                     bitorder="little").view(np.uint64).ravel()
+    assert (q == wq).all() and (s == ws).all()
+
+
+def test_class_bytes_vs_structure_run(ctx):
+    data = bytes(range(256)) * 3 + cases.rand_bytes(16 * 50, 3)
+    got = ctx.class_bytes(data)
+    want = np.concatenate([O.structure_run(data, at) for at in range(0, len(data), 16)])
+    assert (got == want).all()
+
+
+# ---- sharded build: arbitrary cuts, forced inside quotes / between "" / between CR and LF -------
+def _shard_chain(ctx, data, cuts):
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    segs, par, ps = [], 0, []
+    for k in range(len(cuts) - 1):
+        lo, hi = cuts[k], cuts[k + 1]
+        t = torch.from_numpy(np.frombuffer(data, dtype=np.uint8)[lo:hi].copy()).to(dev)
+        p = ctx.shard_quote_parity(t.data_ptr(), hi - lo)
+        idx = ctx.index_build_shard_device(t.data_ptr(), hi - lo, par, lo, emit_sentinel=(k == 0))
+        segs.append(idx.to_host().copy())
+        assert idx.end_parity == par ^ p
+        idx.free()
+        ps.append(p)
+        par ^= p
+    return np.concatenate(segs), ps
+
+
+def test_sharded_equals_single(ctx):
+    data, _ = gen.quoted(3 << 20, seed=44)
+    data = data.tobytes()
+    want = O.closed_form_numpy(data)
+    n = len(data)
+    for G in (2, 4, 8):
+        cuts = [0] + [(k * n) // G + 37 * k + 13 for k in range(1, G)] + [n]
+        got, _ = _shard_chain(ctx, data, cuts)
+        assert got.shape == want.shape and (got == want).all(), G
+
+
+def test_sharded_forced_boundaries(ctx):
+    body = b'id,"text, with ""escapes"" and\r\nnewlines",tail\r\n' * 4000
+    data = b"h1,h2,h3\r\n" + body
+    want = O.closed_form_numpy(data)
+    inside = data.index(b"text")            # (a) inside a quoted field
+    esc = data.index(b'""') + 1             # (b) between the two quotes of ""
+    crlf = data.index(b"\r\n", 50) + 1      # (c) between CR and LF
+    for cut in (inside, esc, crlf, inside + 48 * 1000, esc + 48 * 2001, crlf + 48 * 3999):
+        got, ps = _shard_chain(ctx, data, [0, cut, len(data)])
+        assert (got == want).all(), cut
+    got, _ = _shard_chain(ctx, data, [0, inside, esc, crlf, len(data) // 2 + 5, len(data)])
+    assert (got == want).all()
+
+
+# ---- batched lookups (config 5 in miniature) ------------------------------------------------------
+def test_batched_seeks_vs_oracle(ctx):
+    data, rows = gen.unquoted(2 << 20, seed=45, nfields=256, modulus=10 ** 15)
+    raw = data.tobytes()
+    idx = ctx.index_build(raw, cs.BUILD_KEEP_BYTES)
+    host = idx.to_host()
+    want_idx = O.closed_form_numpy(raw)
+    assert (host == want_idx).all()
+    rc, jump = idx.tape_init(256, False)
+    assert (jump, rc) == O.tape_init(host.size, 256, False) and rc == rows + 1
+    rec, fld = gen.queries(20000, rc, 256, seed=46)
+    # 1 % tail of out-of-range probes must come back as None
+    rec[-200:-100] = rc - 1 + np.arange(100, dtype=np.uint32)
+    fld[-100:] = 256 + np.arange(100, dtype=np.uint32)
+    got = idx.seek_fields(rec, fld)
+    for i in list(range(0, 20000, 97)) + list(range(19800, 20000)):
+        w = O.seek_field(want_idx, len(raw), rc, 256, False, int(rec[i]), int(fld[i]))
+        if w is None:
+            assert got[i, 0] == U64MAX and got[i, 1] == U64MAX
+        else:
+            assert (int(got[i, 0]), int(got[i, 1])) == w
+    # vectorised check of everything in range
+    live = (rec + 1 < rc) & (fld < 256)
+    s = (rec[live].astype(np.int64) + 1) * 256 + fld[live]
+    assert (got[live, 0] == want_idx[s] + 1).all() and (got[live, 1] == want_idx[s + 1]).all()
+    assert (got[~live] == U64MAX).all()
+    gr = idx.seek_records(rec[:500])
+    for i in range(0, 500, 7):
+        w = O.seek_record(want_idx, len(raw), rc, jump, 256, int(rec[i]))
+        assert (int(gr[i, 0]), int(gr[i, 1])) == w
+    offs, blob = idx.gather_fields(rec[:300], fld[:300])
+    for i in range(300):
+        a, b = int(got[i, 0]), int(got[i, 1])
+        assert blob[int(offs[i]):int(offs[i + 1])].tobytes() == raw[a:b]
+    idx.free()
+
+
+def test_crlf_seeks_vs_oracle(ctx):
+    data, rows = gen.quoted(1 << 20, seed=43)
+    raw = data.tobytes()
+    idx = ctx.index_build(raw)
+    host = idx.to_host()
+    # quoted fields contain bare LF / CRLF, so rows are NOT fixed width: InvalidCsvFormat is expected
+    want = O.closed_form_numpy(raw)
+    assert (host == want).all()
+    if (host.size - 1) % 17:
+        with pytest.raises(cs.InvalidCsvFormat):
+            idx.tape_init(16, True)
+    idx.free()
+    body = b"a,\"x,y\",c\r\n" * 5000
+    idx = ctx.index_build(b"h1,h2,h3\r\n" + body)
+    rc, jump = idx.tape_init(3, True)
+    assert (rc, jump) == (5001, 4)
+    host = idx.to_host()
+    raw = b"h1,h2,h3\r\n" + body
+    for r, f in ((0, 0), (0, 1), (0, 2), (4999, 1), (4999, 2), (5000, 0), (17, 3)):
+        w = O.seek_field(host, len(raw), rc, 3, True, r, f)
+        assert idx.seek_field(r, f) == w
+    assert raw[slice(*idx.seek_field(4999, 1))] == b'"x,y"'
+    idx.free()
+
+
+# ---- full-size properties (BASELINE configs 2 and 3) ------------------------------------------------
+@pytest.mark.parametrize("kind", ["cfg2_unquoted", "cfg3_quoted"])
+def test_full_size_properties(ctx, kind):
+    import torch
+    target = 1 << 30
+    if kind == "cfg2_unquoted":
+        data, rows = gen.unquoted(target, seed=42)
+        nf, crlf = 16, False
+    else:
+        data, rows = gen.quoted(target, seed=43)
+        nf, crlf = 16, True
+    n = data.size
+    dev = torch.device("cuda", ctx.device)
+    d = torch.from_numpy(data).to(dev)
+    idx = ctx.index_build_device(d.data_ptr(), n)
+    E = len(idx)
+    # oracle (literal SSE restatement) over the full input: length + checksum (sum of entries mod 2^64)
+    cnt, checksum = O.read_sse_timed(O.aligned_copy(data))
+    assert E == cnt
+    host = idx.to_host()
+    assert int(host.sum(dtype=np.uint64)) == checksum
+    assert host[0] == 0 and (np.diff(host[1:].astype(np.int64)) > 0).all()             # strictly sorted
+    assert np.isin(data[host[1:]], np.array([0x2C, 0x0D, 0x0A], dtype=np.uint8)).all()  # entries are separators
+    if kind == "cfg2_unquoted":
+        rc, jump = idx.tape_init(nf, crlf)
+        assert rc == rows + 1 and jump == 16 and E == 1 + 16 * (rows + 1)
+        assert host[-1] == n - 1
+    # idempotence: a second build of the same bytes gives the same index
+    idx2 = ctx.index_build_device(d.data_ptr(), n)
+    assert len(idx2) == E and (idx2.to_host() == host).all()
+    # sharded at arbitrary offsets == single build (checksum of checksums)
+    G = 4
+    cuts = [0] + [(k * n) // G + 37 * k + 13 for k in range(1, G)] + [n]
+    par, total, csum = 0, 0, 0
+    for k in range(G):
+        lo, hi = cuts[k], cuts[k + 1]
+        lo16 = lo & ~15                      # device pointers handed to the ABI are 16-byte aligned
+        sh = d[lo16:hi]
+        if lo16 != lo:                       # re-materialise the shard at an aligned address
+            sh = d[lo:hi].clone()
+        p = ctx.shard_quote_parity(sh.data_ptr(), hi - lo)
+        si = ctx.index_build_shard_device(sh.data_ptr(), hi - lo, par, lo, emit_sentinel=(k == 0))
+        hs = si.to_host()
+        total += hs.size
+        csum = (csum + int(hs.sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+        par ^= p
+        si.free()
+    assert total == E and csum == checksum
+    idx.free()
+    idx2.free()
