@@ -16,7 +16,7 @@
 // so every tile learns both its carry-in parity and its output base from the
 // same chain and the input is read exactly once.
 //
-// Per tile (16 KiB, 256 threads x 64 B):
+// Per tile (32 KiB, 256 threads x 128 B):
 //   1. coalesced 128-bit loads -> shared memory in the TMA SWIZZLE_128B pattern,
 //      so each thread can read back its own 64 contiguous bytes conflict-free;
 //   2. bit-sliced classification (bitslice.cuh) -> 32-bit quote / separator masks;
@@ -62,9 +62,13 @@ struct WarpState {
     uint32_t off1;  // ... if entered inside quotes
 };
 
-// Shared memory: the input tile (16 KiB) is dead once every thread has pulled its
-// 64 bytes into registers, so the 16-bit staging area of the compaction (worst
-// case one entry per byte = 32 KiB, +1 slot for 16-byte store alignment) aliases it.
+constexpr int kGroups = kBytesPerThread / 32;   // 32-byte bit-slice groups per thread
+constexpr int kChunks = kBytesPerThread / 16;   // 16-byte chunks per thread
+constexpr int kLookbackPerLane = 2;             // descriptors inspected per lane per look-back round
+
+// Shared memory (dynamic): the input tile is dead once every thread has pulled its bytes into
+// registers, so the 16-bit staging area of the compaction (worst case one entry per byte, +8
+// slots of slack for 16-byte store alignment) aliases it.
 struct __align__(1024) Smem {
     union {
         uint8_t in[kTileBytes];
@@ -78,9 +82,10 @@ struct __align__(1024) Smem {
     uint64_t base;
 };
 
-__global__ void __launch_bounds__(kThreads, 4) index_build_kernel(const BuildParams p)
+__global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildParams p)
 {
-    __shared__ Smem sm;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
@@ -91,71 +96,93 @@ __global__ void __launch_bounds__(kThreads, 4) index_build_kernel(const BuildPar
     const uint32_t tile = sm.tile;
     const uint64_t tile_off = (uint64_t)tile * kTileBytes;
 
-    // ---- 1. global -> shared, coalesced, swizzled (chunk' = chunk ^ (row & 7)) ----
-    {
-        uint4 v[4];
+    // ---- 1. global -> shared, coalesced, swizzled (chunk' = chunk ^ (row & 7), the TMA 128B swizzle) ----
+    if (tile_off + kTileBytes <= p.n) {   // full tile: no bounds checks (all tiles but the last)
+        uint4 v[kChunks];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kChunks; ++i) v[i] = ldg_stream_128(p.in + tile_off + 16ull * (tid + kThreads * i));
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const uint32_t c = tid + kThreads * i;
+            *reinterpret_cast<uint4*>(sm.in + 16u * (c ^ ((c >> 3) & 7u))) = v[i];
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < kChunks; ++i) {
             const uint32_t c = tid + kThreads * i;
             const uint64_t goff = tile_off + 16ull * c;
-            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (goff + 16 <= p.n) {
-                v[i] = ldg_stream_128(p.in + goff);
+                v = ldg_stream_128(p.in + goff);
             } else if (goff < p.n) {
                 // the reference zero-pads the final block (avx/stage1.rs:54-57,64-88)
-                uint32_t w[4] = {0u, 0u, 0u, 0u};
                 const uint32_t rem = (uint32_t)(p.n - goff);
-                for (uint32_t b = 0; b < rem; ++b) w[b >> 2] |= (uint32_t)p.in[goff + b] << (8 * (b & 3));
-                v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+                for (uint32_t b = 0; b < rem; ++b) {
+                    const uint32_t byte = (uint32_t)p.in[goff + b] << (8 * (b & 3));
+                    if (b < 4) w0 |= byte;
+                    else if (b < 8) w1 |= byte;
+                    else if (b < 12) w2 |= byte;
+                    else w3 |= byte;
+                }
+                v = make_uint4(w0, w1, w2, w3);
             }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t c = tid + kThreads * i;
-            const uint32_t pc = c ^ ((c >> 3) & 7u);
-            *reinterpret_cast<uint4*>(sm.in + 16u * pc) = v[i];
+            *reinterpret_cast<uint4*>(sm.in + 16u * (c ^ ((c >> 3) & 7u))) = v;
         }
     }
     __syncthreads();
 
-    // ---- 2. each thread: its 64 contiguous bytes -> quote / separator masks ----
-    uint32_t q0, s0, q1, s1;
-    {
-        uint32_t w[16];
+    // ---- 2. each thread: its 128 contiguous bytes (one swizzle row) -> quote / separator masks ----
+    uint32_t q[kGroups], s[kGroups];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t pc = (4u * tid + i) ^ ((tid >> 1) & 7u);
+    for (int g = 0; g < kGroups; ++g) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t c = (uint32_t)kChunks * tid + 2 * g + i;   // logical chunk; row = c >> 3
+            const uint32_t pc = c ^ ((c >> 3) & 7u);
             const uint4 v = *reinterpret_cast<const uint4*>(sm.in + 16u * pc);
             w[4 * i + 0] = v.x;
             w[4 * i + 1] = v.y;
             w[4 * i + 2] = v.z;
             w[4 * i + 3] = v.w;
         }
-        const Masks32 m0 = classify32(w);
-        const Masks32 m1 = classify32(w + 8);
-        q0 = m0.quote;
-        s0 = m0.sep;
-        q1 = m1.quote;
-        s1 = m1.sep;
+        const Masks32 m = classify32(w);
+        q[g] = m.quote;
+        s[g] = m.sep;
     }
 
     // ---- 3. quote regions inside the warp (relative to the warp start) ----
     // x = inclusive prefix-XOR of the quote bits: opening quote bit = 1, closing = 0,
     // exactly the reference's string_mask (avx/stage1.rs:397).
-    uint32_t x0 = 0u, x1 = 0u, warp_par = 0u;
-    if (__any_sync(0xffffffffu, (q0 | q1) != 0u)) {
-        x0 = prefix_xor32(q0);
-        x1 = prefix_xor32(q1) ^ (0u - (x0 >> 31));
-        const uint32_t bal = __ballot_sync(0xffffffffu, (x1 >> 31) != 0u);
+    uint32_t x[kGroups];
+    uint32_t warp_par = 0u, anyq = 0u;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        x[g] = 0u;
+        anyq |= q[g];
+    }
+    if (__any_sync(0xffffffffu, anyq != 0u)) {
+        uint32_t carry = 0u;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            x[g] = prefix_xor32(q[g]) ^ carry;
+            carry = 0u - (x[g] >> 31);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, carry != 0u);
         const uint32_t lane_in = __popc(bal & ((1u << lane) - 1u)) & 1u;
         warp_par = __popc(bal) & 1u;
         const uint32_t flip = 0u - lane_in;
-        x0 ^= flip;
-        x1 ^= flip;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) x[g] ^= flip;
     }
     // counts under "warp entered outside quotes" (a0) and the hypothesis-free total (tt)
-    const uint32_t a0 = __popc(s0 & ~x0) + __popc(s1 & ~x1);
-    const uint32_t tt = __popc(s0) + __popc(s1);
+    uint32_t a0 = 0u, tt = 0u;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        a0 += __popc(s[g] & ~x[g]);
+        tt += __popc(s[g]);
+    }
     const uint32_t packed = a0 | (tt << 16);
     uint32_t inc = packed;
 #pragma unroll
@@ -203,45 +230,64 @@ __global__ void __launch_bounds__(kThreads, 4) index_build_kernel(const BuildPar
             return kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
         };
 
-        // suffix composite S of the tiles already absorbed (those nearest to us)
+        // Suffix composite S = (sp, sc0, sc1) of the tiles already absorbed (those nearest to us).
+        // Every round inspects 32 * kLookbackPerLane predecessors: sub-window k holds tiles
+        // idx0 - 32k - lane, nearest first, and is folded in only while no prefix has been met.
         uint32_t sp = 0u;
         uint64_t sc0 = 0ull, sc1 = 0ull;
-        int64_t idx = (int64_t)tile - 1 - (int64_t)lane;
-        uint32_t pin;
-        uint64_t base;
-        while (true) {
-            const uint64_t d = idx >= 0 ? ld_relaxed_u64(p.desc + idx) : virtual_prefix();
-            const uint32_t status = (uint32_t)(d >> 62);
-            const uint32_t pref = __ballot_sync(0xffffffffu, status == 2u);
-            const uint32_t inval = __ballot_sync(0xffffffffu, status == 0u);
-            const uint32_t lp = pref ? (uint32_t)(__ffs(pref) - 1) : 32u;       // nearest prefix lane
-            const uint32_t need = lp >= 32u ? 0xffffffffu : ((1u << lp) - 1u);  // lanes that must be aggregates
-            if (inval & need) continue;                                         // predecessor not published yet
-            const bool in_win = lane < lp;
-            const uint32_t pj = in_win ? (uint32_t)((d >> 61) & 1ull) : 0u;
-            const uint32_t c0j = (uint32_t)(d & 0xfffffull), c1j = (uint32_t)((d >> 20) & 0xfffffull);
-            const uint32_t bp = __ballot_sync(0xffffffffu, pj != 0u);
-            // parity accumulated by the window tiles EARLIER than mine (= higher lanes)
-            const uint32_t rel = __popc(bp & (0xfffffffeu << lane)) & 1u;
-            const uint32_t w0j = in_win ? (rel ? c1j : c0j) : 0u;
-            const uint32_t w1j = in_win ? (rel ? c0j : c1j) : 0u;
-            const uint32_t W0 = __reduce_add_sync(0xffffffffu, w0j);
-            const uint32_t W1 = __reduce_add_sync(0xffffffffu, w1j);
-            const uint32_t Wp = __popc(bp) & 1u;
-            // S <- W o S   (window is earlier in the file than everything absorbed so far)
-            const uint64_t n0 = (uint64_t)W0 + (Wp ? sc1 : sc0);
-            const uint64_t n1 = (uint64_t)W1 + (Wp ? sc0 : sc1);
-            sc0 = n0;
-            sc1 = n1;
-            sp ^= Wp;
-            if (pref) {
-                const uint64_t pd = __shfl_sync(0xffffffffu, d, (int)lp);
-                const uint32_t P = (uint32_t)((pd >> 61) & 1ull);
-                pin = P ^ sp;
-                base = (pd & kCountMask) + (P ? sc1 : sc0);
-                break;
+        int64_t idx0 = (int64_t)tile - 1;
+        uint32_t pin = 0u;
+        uint64_t base = 0ull;
+        bool done = false;
+        while (!done) {
+            uint64_t d[kLookbackPerLane];
+#pragma unroll
+            for (int k = 0; k < kLookbackPerLane; ++k) {
+                const int64_t idx = idx0 - 32 * k - (int64_t)lane;
+                d[k] = idx >= 0 ? ld_relaxed_u64(p.desc + idx) : virtual_prefix();
             }
-            idx -= 32;
+            int absorbed = 0;
+            bool stop = false;
+#pragma unroll
+            for (int k = 0; k < kLookbackPerLane; ++k) {
+                if (stop) continue;
+                const uint32_t status = (uint32_t)(d[k] >> 62);
+                const uint32_t pref = __ballot_sync(0xffffffffu, status == 2u);
+                const uint32_t inval = __ballot_sync(0xffffffffu, status == 0u);
+                const uint32_t lp = pref ? (uint32_t)(__ffs(pref) - 1) : 32u;       // nearest prefix lane
+                const uint32_t need = lp >= 32u ? 0xffffffffu : ((1u << lp) - 1u);  // lanes that must be aggregates
+                if (inval & need) {                                                 // not published yet: re-poll
+                    stop = true;
+                    continue;
+                }
+                const bool in_win = lane < lp;
+                const uint32_t pj = in_win ? (uint32_t)((d[k] >> 61) & 1ull) : 0u;
+                const uint32_t c0j = (uint32_t)(d[k] & 0xfffffull), c1j = (uint32_t)((d[k] >> 20) & 0xfffffull);
+                const uint32_t bp = __ballot_sync(0xffffffffu, pj != 0u);
+                // parity accumulated by the window tiles EARLIER than mine (= higher lanes)
+                const uint32_t rel = __popc(bp & (0xfffffffeu << lane)) & 1u;
+                const uint32_t w0j = in_win ? (rel ? c1j : c0j) : 0u;
+                const uint32_t w1j = in_win ? (rel ? c0j : c1j) : 0u;
+                const uint32_t W0 = __reduce_add_sync(0xffffffffu, w0j);
+                const uint32_t W1 = __reduce_add_sync(0xffffffffu, w1j);
+                const uint32_t Wp = __popc(bp) & 1u;
+                // S <- W o S   (the window is earlier in the file than everything absorbed so far)
+                const uint64_t n0 = (uint64_t)W0 + (Wp ? sc1 : sc0);
+                const uint64_t n1 = (uint64_t)W1 + (Wp ? sc0 : sc1);
+                sc0 = n0;
+                sc1 = n1;
+                sp ^= Wp;
+                ++absorbed;
+                if (pref) {
+                    const uint64_t pd = __shfl_sync(0xffffffffu, d[k], (int)lp);
+                    const uint32_t P = (uint32_t)((pd >> 61) & 1ull);
+                    pin = P ^ sp;
+                    base = (pd & kCountMask) + (P ? sc1 : sc0);
+                    done = true;
+                    stop = true;
+                }
+            }
+            idx0 -= 32 * absorbed;
         }
         if (lane == 0) {
             const uint32_t pend = pin ^ par;
@@ -272,37 +318,39 @@ __global__ void __launch_bounds__(kThreads, 4) index_build_kernel(const BuildPar
     {
         const WarpState ws = sm.warp_state[warp];
         const uint32_t h = pin ^ ws.par;                 // parity entering this warp
-        const uint32_t ex_a0 = exc & 0x7fffu, ex_tt = (exc >> 16) & 0x7fffu;
-        uint32_t slot = head + (pin ? ws.off1 : ws.off0) + (h ? ex_tt - ex_a0 : ex_a0);
+        const uint32_t ex_a0 = exc & 0xffffu, ex_tt = exc >> 16;
+        uint16_t* dst = sm.stage + head + (pin ? ws.off1 : ws.off0) + (h ? ex_tt - ex_a0 : ex_a0);
         const uint32_t flip = 0u - h;
-        // structure = all_struct & !string_mask (avx/stage1.rs:400-406)
-        uint32_t m0 = s0 & ~(x0 ^ flip);
-        uint32_t m1 = s1 & ~(x1 ^ flip);
-        const uint32_t rel0 = tid * kBytesPerThread;
-        while (m0) {
-            sm.stage[slot++] = (uint16_t)(rel0 + (uint32_t)__ffs((int)m0) - 1u);
-            m0 &= m0 - 1u;  // blsr (stage1.rs:239)
-        }
-        while (m1) {
-            sm.stage[slot++] = (uint16_t)(rel0 + 32u + (uint32_t)__ffs((int)m1) - 1u);
-            m1 &= m1 - 1u;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            // structure = all_struct & !string_mask (avx/stage1.rs:400-406)
+            uint32_t m = s[g] & ~(x[g] ^ flip);
+            const uint32_t rel0 = tid * kBytesPerThread + 32u * g;
+            while (m) {
+                *dst++ = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
+                m &= m - 1u;  // blsr (stage1.rs:239)
+            }
         }
     }
     __syncthreads();
     {
         const uint64_t tile_pos = p.pos_bias + tile_off;
         if (head && tid == 0 && cnt > 0 && g0 < p.cap) p.index[g0] = tile_pos + sm.stage[1];
-        // staging index j = i + head is even for every pair
+        // staging index j = i + head is even for every pair, and g = g0 - head + j is even too
         const uint32_t end = cnt + head;
-        for (uint32_t j = 2u * head + 2u * tid; j < end; j += 2u * kThreads) {
-            const uint64_t g = g0 + (j - head);
-            const uint32_t pr = *reinterpret_cast<const uint32_t*>(&sm.stage[j]);
-            const uint64_t e0 = tile_pos + (pr & 0xffffu);
-            if (j + 1 < end && g + 1 < p.cap) {
-                stg_128(p.index + g, e0, tile_pos + (pr >> 16));
-            } else if (g < p.cap) {
-                p.index[g] = e0;
+        const uint64_t gbase = g0 - head;
+        uint64_t* out = p.index + gbase;
+        if (gbase + end <= p.cap) {
+            // common case: the whole run fits; full 16-byte stores except possibly the last entry
+            const uint32_t end2 = end & ~1u;
+            for (uint32_t j = 2u * head + 2u * tid; j < end2; j += 2u * kThreads) {
+                const uint32_t pr = *reinterpret_cast<const uint32_t*>(&sm.stage[j]);
+                stg_128(out + j, tile_pos + (pr & 0xffffu), tile_pos + (pr >> 16));
             }
+            if ((end & 1u) && tid == 0 && end > 2u * head) out[end - 1] = tile_pos + sm.stage[end - 1];
+        } else {
+            for (uint32_t j = 2u * head + tid; j < end; j += kThreads)
+                if (gbase + j < p.cap) out[j] = tile_pos + sm.stage[j];
         }
     }
 }
@@ -378,7 +426,14 @@ __global__ void class_bytes_kernel(const uint8_t* __restrict__ in, uint64_t n, u
 cudaError_t launch_index_build(const BuildParams& p, cudaStream_t stream)
 {
     if (p.num_tiles == 0) return cudaSuccess;
-    index_build_kernel<<<p.num_tiles, kThreads, 0, stream>>>(p);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(index_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    index_build_kernel<<<p.num_tiles, kThreads, sizeof(Smem), stream>>>(p);
     return cudaGetLastError();
 }
 

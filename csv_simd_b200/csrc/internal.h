@@ -8,8 +8,8 @@ namespace csvb200 {
 
 // ---- tile geometry of the fused index-build kernel --------------------------
 constexpr int kThreads = 256;                              // threads per CTA
-constexpr int kBytesPerThread = 64;                        // two 32-byte bit-slice groups
-constexpr int kTileBytes = kThreads * kBytesPerThread;     // 16 KiB of CSV per tile
+constexpr int kBytesPerThread = 128;                       // four 32-byte bit-slice groups = one 128 B swizzle row
+constexpr int kTileBytes = kThreads * kBytesPerThread;     // 32 KiB of CSV per tile
 constexpr int kWarps = kThreads / 32;
 
 // ---- look-back descriptor (one u64 per tile, written/read as a single word) --

@@ -4,7 +4,7 @@ from __future__ import annotations
 import numpy as np
 
 ALPHABET = np.frombuffer(b'ab1,"\r\n \\\x00\xff', dtype=np.uint8)
-TILE = 16384
+TILE = 32768  # kTileBytes of the CUDA kernel (also exercises multiples of the older 16 KiB tile)
 
 
 def rand_bytes(n: int, seed: int, weights=None) -> bytes:
