@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -40,6 +41,8 @@ struct csvb200_ctx {
     cudaEvent_t stage_free[kStageBufs] = {nullptr, nullptr};
     uint32_t reserve_num = 1, reserve_den = 3;
     uint64_t launches = 0;
+    int kernel_override = 0;  // 0 = auto, 1 = simple, 2 = tma (CSVB200_KERNEL)
+    uint32_t tune = 0;        // CSVB200_TUNE experiment knob
     std::string err;
 };
 
@@ -121,7 +124,7 @@ int enqueue_build(csvb200_index* idx, bool timed)
         h_cell[0] = 0;
         h_cell[1] = idx->carry_parity;
     } else {
-        const size_t sbytes = 16 + num_tiles * sizeof(uint64_t);
+        const size_t sbytes = 128 + num_tiles * kDescStride * sizeof(uint64_t);
         int rc = ensure_scratch(ctx, sbytes);
         if (rc) return rc;
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, ctx->stream));
@@ -137,13 +140,22 @@ int enqueue_build(csvb200_index* idx, bool timed)
         p.carry_parity = idx->carry_parity;
         p.num_tiles = (uint32_t)num_tiles;
         p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
-        p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 16);
+        p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
         p.result = d_cell;
         p.result2 = idx->d_result2;
         p.shard_par = idx->d_shard_par;
         p.shard_rank = idx->shard_rank;
+        p.tune = ctx->tune;
         if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
-        CU_TRY(ctx, launch_index_build(p, ctx->stream));
+        // kernel choice: the TMA pipeline for anything of size, the one-tile-per-CTA kernel for small
+        // inputs; CSVB200_KERNEL=simple|tma forces one (tests cross-check the two against each other)
+        bool use_tma = tma_path_usable(n);
+        if (ctx->kernel_override == 1) use_tma = false;
+        if (ctx->kernel_override == 2 && n >= 128) use_tma = true;
+        if (use_tma)
+            CU_TRY(ctx, launch_index_build_tma(p, ctx->stream));
+        else
+            CU_TRY(ctx, launch_index_build(p, ctx->stream));
         ctx->launches += 1;
         if (timed) {
             CU_TRY(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
@@ -276,6 +288,11 @@ int csvb200_ctx_create(int device, csvb200_ctx** out)
     csvb200_ctx* ctx = new (std::nothrow) csvb200_ctx();
     if (!ctx) return CSVB200_ERR_OOM;
     ctx->device = device;
+    if (const char* k = std::getenv("CSVB200_KERNEL")) {
+        if (std::strcmp(k, "simple") == 0) ctx->kernel_override = 1;
+        if (std::strcmp(k, "tma") == 0) ctx->kernel_override = 2;
+    }
+    if (const char* t = std::getenv("CSVB200_TUNE")) ctx->tune = (uint32_t)std::atoi(t);
     auto bail = [&](cudaError_t) {
         cudaGetLastError();
         csvb200_ctx_destroy(ctx);

@@ -26,45 +26,11 @@
 //   5. ordered compaction: every thread expands its mask into 16-bit tile-relative
 //      offsets in shared memory at its scanned slot, then the CTA streams the tile's
 //      run out as full 16-byte stores (2 entries) of pos_bias + tile_base + offset.
-#include "bitslice.cuh"
-#include "internal.h"
+#include "index_common.cuh"
 
 namespace csvb200 {
 
 namespace {
-
-__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p)
-{
-    uint64_t v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint4 ldg_stream_128(const void* p)
-{
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void stg_128(void* p, uint64_t a, uint64_t b)
-{
-    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-
-struct WarpState {
-    uint32_t par;   // quote parity of the warps before this one (relative to tile start)
-    uint32_t off0;  // entries emitted by those warps if the tile is entered outside quotes
-    uint32_t off1;  // ... if entered inside quotes
-};
-
-constexpr int kGroups = kBytesPerThread / 32;   // 32-byte bit-slice groups per thread
-constexpr int kChunks = kBytesPerThread / 16;   // 16-byte chunks per thread
-constexpr int kLookbackPerLane = 2;             // descriptors inspected per lane per look-back round
 
 // Shared memory (dynamic): the input tile is dead once every thread has pulled its bytes into
 // registers, so the 16-bit staging area of the compaction (worst case one entry per byte, +8
@@ -212,87 +178,18 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
         }
         // (par, o0, o1) is the tile aggregate
         if (lane == 0)
-            st_relaxed_u64(p.desc + tile, kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
+            st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride, kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
 
-        // virtual predecessor of tile 0: the carry entering this launch (only tiles whose look-back
-        // window reaches below tile 0 ever evaluate it)
-        auto virtual_prefix = [&]() -> uint64_t {
-            uint64_t carry_count = p.carry_count;
-            uint32_t carry_parity = p.carry_parity;
-            if (p.carry != nullptr) {
-                carry_count = p.carry[0];
-                carry_parity = (uint32_t)p.carry[1] & 1u;
-            }
-            if (p.shard_par != nullptr) {
-                carry_parity = 0u;
-                for (uint32_t j = 0; j < p.shard_rank; ++j) carry_parity ^= p.shard_par[j] & 1u;
-            }
-            return kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
-        };
-
-        // Suffix composite S = (sp, sc0, sc1) of the tiles already absorbed (those nearest to us).
-        // Every round inspects 32 * kLookbackPerLane predecessors: sub-window k holds tiles
-        // idx0 - 32k - lane, nearest first, and is folded in only while no prefix has been met.
-        uint32_t sp = 0u;
-        uint64_t sc0 = 0ull, sc1 = 0ull;
-        int64_t idx0 = (int64_t)tile - 1;
-        uint32_t pin = 0u;
-        uint64_t base = 0ull;
-        bool done = false;
-        while (!done) {
-            uint64_t d[kLookbackPerLane];
-#pragma unroll
-            for (int k = 0; k < kLookbackPerLane; ++k) {
-                const int64_t idx = idx0 - 32 * k - (int64_t)lane;
-                d[k] = idx >= 0 ? ld_relaxed_u64(p.desc + idx) : virtual_prefix();
-            }
-            int absorbed = 0;
-            bool stop = false;
-#pragma unroll
-            for (int k = 0; k < kLookbackPerLane; ++k) {
-                if (stop) continue;
-                const uint32_t status = (uint32_t)(d[k] >> 62);
-                const uint32_t pref = __ballot_sync(0xffffffffu, status == 2u);
-                const uint32_t inval = __ballot_sync(0xffffffffu, status == 0u);
-                const uint32_t lp = pref ? (uint32_t)(__ffs(pref) - 1) : 32u;       // nearest prefix lane
-                const uint32_t need = lp >= 32u ? 0xffffffffu : ((1u << lp) - 1u);  // lanes that must be aggregates
-                if (inval & need) {                                                 // not published yet: re-poll
-                    stop = true;
-                    continue;
-                }
-                const bool in_win = lane < lp;
-                const uint32_t pj = in_win ? (uint32_t)((d[k] >> 61) & 1ull) : 0u;
-                const uint32_t c0j = (uint32_t)(d[k] & 0xfffffull), c1j = (uint32_t)((d[k] >> 20) & 0xfffffull);
-                const uint32_t bp = __ballot_sync(0xffffffffu, pj != 0u);
-                // parity accumulated by the window tiles EARLIER than mine (= higher lanes)
-                const uint32_t rel = __popc(bp & (0xfffffffeu << lane)) & 1u;
-                const uint32_t w0j = in_win ? (rel ? c1j : c0j) : 0u;
-                const uint32_t w1j = in_win ? (rel ? c0j : c1j) : 0u;
-                const uint32_t W0 = __reduce_add_sync(0xffffffffu, w0j);
-                const uint32_t W1 = __reduce_add_sync(0xffffffffu, w1j);
-                const uint32_t Wp = __popc(bp) & 1u;
-                // S <- W o S   (the window is earlier in the file than everything absorbed so far)
-                const uint64_t n0 = (uint64_t)W0 + (Wp ? sc1 : sc0);
-                const uint64_t n1 = (uint64_t)W1 + (Wp ? sc0 : sc1);
-                sc0 = n0;
-                sc1 = n1;
-                sp ^= Wp;
-                ++absorbed;
-                if (pref) {
-                    const uint64_t pd = __shfl_sync(0xffffffffu, d[k], (int)lp);
-                    const uint32_t P = (uint32_t)((pd >> 61) & 1ull);
-                    pin = P ^ sp;
-                    base = (pd & kCountMask) + (P ? sc1 : sc0);
-                    done = true;
-                    stop = true;
-                }
-            }
-            idx0 -= 32 * absorbed;
-        }
+        uint32_t pin;
+        uint64_t base;
+        if (p.tune == 2)
+            decoupled_lookback<2>(p, tile, lane, pin, base);
+        else
+            decoupled_lookback<1>(p, tile, lane, pin, base);
         if (lane == 0) {
             const uint32_t pend = pin ^ par;
             const uint64_t cend = base + (pin ? o1 : o0);
-            st_relaxed_u64(p.desc + tile, kStatusPrefix | (pend ? kParityBit : 0ull) | (cend & kCountMask));
+            st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride, kStatusPrefix | (pend ? kParityBit : 0ull) | (cend & kCountMask));
             sm.pin = pin;
             sm.base = base;
             sm.tot0 = o0;

@@ -1,0 +1,443 @@
+// index_build_tma.cu -- persistent, warp-specialised, TMA-fed version of the fused index build.
+//
+// Same algorithm and output as index_build.cu (see its header for the reference mapping:
+// reader::read src/reader.rs:150-306, SimdInput::structure src/avx/stage1.rs:193-407,
+// Stage1::crush_set_bits src/stage1.rs:162-296), re-organised around what bounds it on B200:
+//
+//   * ncu on the one-tile-per-CTA kernel showed >50 % of warp stalls at the barrier behind the
+//     decoupled look-back and a load stage that needs registers + LSU slots.  Here the CTA is
+//     persistent (2 per SM) and split into roles:
+//       warps 0-7  workers : classify / scan / compact            (256 threads x 128 B = 32 KiB tile)
+//       warp  8    producer: takes tile tickets, issues one TMA 2-D tile load per tile
+//                            (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier complete_tx)
+//       warp  9    look-back: scans the 8 warp aggregates, publishes the tile descriptor, runs the
+//                            warp-parallel decoupled look-back, hands (parity, base) to the workers
+//   * the compaction of tile k is skewed behind the classification of tile k+1, so the look-back
+//     latency (a few L2 round trips) is covered by useful work instead of a barrier stall;
+//   * the input is a 2-D tensor map [rows = n/128][128 B]; rows past the end are zero-filled by
+//     the TMA unit, which reproduces the reference's zero padding of the last block
+//     (src/avx/stage1.rs:54-88) for free; the sub-row tail (< 128 B) is patched in by one thread.
+#include <cuda.h>
+
+#include "index_common.cuh"
+
+namespace csvb200 {
+
+namespace {
+
+constexpr int kWorkerWarps = kWarps;             // 8
+constexpr int kProducerWarp = kWorkerWarps;      // warp 8
+constexpr int kLookbackWarp = kWorkerWarps + 1;  // warp 9
+constexpr int kTmaThreads = kThreads + 64;       // 320
+constexpr int kStages = 2;                       // TMA ring depth (x 2 CTAs/SM = 128 KiB in flight per SM)
+constexpr int kStageCap = 8192;                  // entries per staging buffer; denser tiles take extra rounds
+constexpr int kRowsPerTile = kTileBytes / 128;   // 256 = max TMA box extent
+constexpr int kSkew = 2;                         // tiles classified ahead of the tile being compacted
+constexpr int kRing = kSkew + 1;                 // ring depth of the worker <-> look-back hand-off buffers
+constexpr uint32_t kInvalidTile = 0xffffffffu;
+
+struct PrefixInfo {
+    uint32_t pin;    // quote parity entering the tile
+    uint32_t tot0;   // entries of the tile if entered outside quotes
+    uint32_t tot1;   // ... inside quotes
+    uint32_t pad;
+    uint64_t base;   // entries emitted before the tile
+    WarpState ws[kWorkerWarps];
+};
+
+struct __align__(1024) SmemTma {
+    uint8_t in[kStages][kTileBytes];        // TMA destinations, 1024-byte aligned (SWIZZLE_128B)
+    uint16_t stage[2][kStageCap + 8];       // 16-bit tile-relative offsets, double buffered by tile parity
+    uint64_t full[kStages];                 // producer -> workers (TMA complete_tx)
+    uint64_t empty[kStages];                // workers -> producer
+    uint64_t agg_full[kRing];               // workers -> look-back warp
+    uint64_t pref_full[kRing];              // look-back warp -> workers
+    uint32_t tile_id[kStages];
+    uint32_t agg_tile[kRing];
+    uint32_t warp_agg[kRing][kWorkerWarps];
+    PrefixInfo pref[kRing];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap* tmap, int32_t c0, int32_t c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+
+// streams staged entries [j0, j1) (staging indices, j0 even) of a run whose staging index 0 maps to
+// global slot `out`; positions are tile_pos + 16-bit offset
+__device__ __forceinline__ void copy_out_range(const BuildParams& p, const uint16_t* stg, uint32_t local0, uint32_t j0,
+                                               uint32_t j1, uint64_t gbase, uint64_t tile_pos, uint32_t tid)
+{
+    uint64_t* out = p.index + gbase;
+    if (gbase + j1 <= p.cap) {
+        const uint32_t j1e = j1 & ~1u;
+        for (uint32_t j = j0 + 2u * tid; j < j1e; j += 2u * kThreads) {
+            const uint32_t pr = *reinterpret_cast<const uint32_t*>(&stg[j - local0]);
+            stg_128(out + j, tile_pos + (pr & 0xffffu), tile_pos + (pr >> 16));
+        }
+        if ((j1 & 1u) && tid == 0 && j1 > j0) out[j1 - 1] = tile_pos + stg[j1 - 1 - local0];
+    } else {
+        for (uint32_t j = j0 + tid; j < j1; j += kThreads)
+            if (gbase + j < p.cap) out[j] = tile_pos + stg[j - local0];
+    }
+}
+
+// per-thread state of a classified tile awaiting compaction
+struct TileRegs {
+    uint32_t s[kGroups];   // separator masks
+    uint32_t x[kGroups];   // in-string masks relative to the warp start
+    uint32_t exc;          // packed exclusive warp scan: entries before this thread (outside-hypothesis | total << 16)
+    uint32_t tile;
+};
+
+// Ordered compaction of one tile (the `it`-th tile this CTA processed): wait for its (parity, base)
+// from the look-back warp, expand the masks into 16-bit offsets in shared memory at the scanned
+// slots, then stream the run out as 16-byte stores.
+__device__ __forceinline__ void compact_tile(SmemTma& sm, const BuildParams& p, const TileRegs& t, uint32_t it, uint32_t tid,
+                                             uint32_t lane, uint32_t warp)
+{
+    (void)lane;
+    const uint32_t pb = it % kRing;
+    mbar_wait(&sm.pref_full[pb], (it / kRing) & 1u);
+    const PrefixInfo& pi = sm.pref[pb];
+    const uint32_t pin = pi.pin;
+    const uint32_t cnt = pin ? pi.tot1 : pi.tot0;
+    const uint64_t g0 = p.out_base + pi.base;       // slot of the tile's first entry
+    const uint32_t head = (uint32_t)(g0 & 1ull);     // keep even slots on even staging indices
+    const uint32_t end = cnt + head;
+    const uint64_t gbase = g0 - head;
+    const uint64_t tile_pos = p.pos_bias + (uint64_t)t.tile * kTileBytes;
+    const WarpState ws = pi.ws[warp];
+    const uint32_t h = pin ^ ws.par;                 // parity entering this warp
+    const uint32_t ex_a0 = t.exc & 0xffffu, ex_tt = t.exc >> 16;
+    const uint32_t slot0 = head + (pin ? ws.off1 : ws.off0) + (h ? ex_tt - ex_a0 : ex_a0);
+    const uint32_t flip = 0u - h;
+    uint16_t* stg = sm.stage[it & 1u];
+    if (end <= (uint32_t)kStageCap) {
+        uint16_t* dst = stg + slot0;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            uint32_t m = t.s[g] & ~(t.x[g] ^ flip);   // structure = all_struct & !string_mask (avx/stage1.rs:400-406)
+            const uint32_t rel0 = tid * kBytesPerThread + 32u * g;
+            while (m) {
+                *dst++ = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
+                m &= m - 1u;  // blsr (stage1.rs:239)
+            }
+        }
+        worker_barrier();
+        if (head && tid == 0 && cnt > 0 && g0 < p.cap) p.index[g0] = tile_pos + stg[1];
+        copy_out_range(p, stg, 0u, 2u * head, end, gbase, tile_pos, tid);
+        // no trailing barrier: this staging buffer is next written two compactions from now,
+        // behind the other buffer's worker_barrier()
+    } else {
+        // dense tile (more than kStageCap entries): several staging rounds
+        for (uint32_t r0 = 0; r0 < end; r0 += (uint32_t)kStageCap) {
+            uint32_t slot = slot0;
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                uint32_t m = t.s[g] & ~(t.x[g] ^ flip);
+                const uint32_t rel0 = tid * kBytesPerThread + 32u * g;
+                while (m) {
+                    if (slot - r0 < (uint32_t)kStageCap) stg[slot - r0] = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
+                    ++slot;
+                    m &= m - 1u;
+                }
+            }
+            worker_barrier();
+            const uint32_t r1 = min(end, r0 + (uint32_t)kStageCap);
+            if (r0 == 0 && head && tid == 0 && cnt > 0 && g0 < p.cap) p.index[g0] = tile_pos + stg[1];
+            copy_out_range(p, stg, r0, r0 == 0 ? 2u * head : r0, r1, gbase, tile_pos, tid);
+            worker_barrier();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 2)
+index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemTma& sm = *reinterpret_cast<SmemTma*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], kWorkerWarps);
+        }
+#pragma unroll
+        for (int i = 0; i < kRing; ++i) {
+            mbar_init(&sm.agg_full[i], kWorkerWarps);
+            mbar_init(&sm.pref_full[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kProducerWarp) {
+        // ===== TMA producer: one elected lane =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t st = it % kStages;
+                mbar_wait(&sm.empty[st], ((it / kStages) & 1u) ^ 1u);
+                // dynamic tile id: a tile only ever waits on tiles whose CTAs already hold a ticket
+                const uint32_t tile = atomicAdd(p.ticket, 1u);
+                if (tile >= p.num_tiles) {
+                    sm.tile_id[st] = kInvalidTile;
+                    mbar_arrive(&sm.full[st]);
+                    break;
+                }
+                sm.tile_id[st] = tile;
+                mbar_arrive_expect_tx(&sm.full[st], (uint32_t)kTileBytes);
+                tma_load_tile(sm.in[st], &tmap, 0, (int32_t)(tile * (uint32_t)kRowsPerTile), &sm.full[st]);
+            }
+        }
+    } else if (warp == kLookbackWarp) {
+        // ===== scan of warp aggregates + decoupled look-back =====
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t b = it % kRing;
+            mbar_wait(&sm.agg_full[b], (it / kRing) & 1u);
+            const uint32_t tile = sm.agg_tile[b];
+            if (tile == kInvalidTile) break;
+            uint32_t par = 0u, o0 = 0u, o1 = 0u;
+#pragma unroll
+            for (int w = 0; w < kWorkerWarps; ++w) {
+                const uint32_t v = sm.warp_agg[b][w];
+                const uint32_t wa0 = v & 0x7fffu, wt = (v >> 16) & 0x7fffu, wa1 = wt - wa0;
+                if (lane == 0) {
+                    sm.pref[b].ws[w].par = par;
+                    sm.pref[b].ws[w].off0 = o0;
+                    sm.pref[b].ws[w].off1 = o1;
+                }
+                o0 += par ? wa1 : wa0;
+                o1 += par ? wa0 : wa1;
+                par ^= v >> 31;
+            }
+            if (lane == 0)
+                st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride,
+                               kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
+            uint32_t pin;
+            uint64_t base;
+            switch (p.tune) {
+            case 2: decoupled_lookback<2>(p, tile, lane, pin, base); break;
+            case 4: decoupled_lookback<4>(p, tile, lane, pin, base); break;
+            default: decoupled_lookback<1>(p, tile, lane, pin, base); break;  // measured best: 0.45 / 0.48 / 0.59 ms for 1 / 2 / 4
+            }
+            if (lane == 0) {
+                const uint32_t pend = pin ^ par;
+                const uint64_t cend = base + (pin ? o1 : o0);
+                st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride, kStatusPrefix | (pend ? kParityBit : 0ull) | (cend & kCountMask));
+                sm.pref[b].pin = pin;
+                sm.pref[b].base = base;
+                sm.pref[b].tot0 = o0;
+                sm.pref[b].tot1 = o1;
+                if (tile == p.num_tiles - 1) {
+                    p.result[0] = cend;
+                    p.result[1] = pend;
+                    if (p.result2 != nullptr) {
+                        p.result2[0] = cend;
+                        p.result2[1] = pend;
+                    }
+                }
+                mbar_arrive(&sm.pref_full[b]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== workers =====
+        const uint64_t full_rows = p.n >> 7;
+        const uint32_t tail = (uint32_t)(p.n & 127u);
+        // masks of the tiles that are classified but not yet compacted (kSkew of them, oldest first)
+        TileRegs pend[kSkew];
+#pragma unroll
+        for (int k = 0; k < kSkew; ++k) pend[k].tile = kInvalidTile;
+
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t st = it % kStages, b = it % kRing;
+            mbar_wait(&sm.full[st], (it / kStages) & 1u);
+            const uint32_t tile = sm.tile_id[st];
+            TileRegs cur;
+            cur.tile = tile;
+            cur.exc = 0u;
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) cur.s[g] = cur.x[g] = 0u;
+
+            if (tile != kInvalidTile) {
+                uint8_t* in = sm.in[st];
+                // the sub-row tail of the file is outside the tensor map: its owner patches it in
+                if (tail != 0u && (uint64_t)tile * kRowsPerTile + tid == full_rows) {
+                    for (uint32_t k = 0; k < tail; ++k) {
+                        const uint32_t c = (uint32_t)kChunks * tid + (k >> 4);
+                        in[16u * (c ^ ((c >> 3) & 7u)) + (k & 15u)] = p.in[full_rows * 128u + k];
+                    }
+                }
+                // ---- classify: 128 contiguous bytes (one swizzle row) per thread ----
+                uint32_t q[kGroups];
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint32_t c = (uint32_t)kChunks * tid + 2 * g + i;
+                        const uint4 v = *reinterpret_cast<const uint4*>(in + 16u * (c ^ ((c >> 3) & 7u)));
+                        w[4 * i + 0] = v.x;
+                        w[4 * i + 1] = v.y;
+                        w[4 * i + 2] = v.z;
+                        w[4 * i + 3] = v.w;
+                    }
+                    const Masks32 m = classify32(w);
+                    q[g] = m.quote;
+                    cur.s[g] = m.sep;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[st]);  // stage can be refilled
+
+                // ---- quote regions relative to the warp start (string_mask, avx/stage1.rs:397) ----
+                uint32_t warp_par = 0u, anyq = 0u;
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) anyq |= q[g];
+                if (__any_sync(0xffffffffu, anyq != 0u)) {
+                    uint32_t carry = 0u;
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        cur.x[g] = prefix_xor32(q[g]) ^ carry;
+                        carry = 0u - (cur.x[g] >> 31);
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, carry != 0u);
+                    const uint32_t lane_in = __popc(bal & ((1u << lane) - 1u)) & 1u;
+                    warp_par = __popc(bal) & 1u;
+                    const uint32_t flip = 0u - lane_in;
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) cur.x[g] ^= flip;
+                }
+                uint32_t a0 = 0u, tt = 0u;
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    a0 += __popc(cur.s[g] & ~cur.x[g]);
+                    tt += __popc(cur.s[g]);
+                }
+                const uint32_t packed = a0 | (tt << 16);
+                uint32_t inc = packed;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= (uint32_t)d) inc += v;
+                }
+                cur.exc = inc - packed;
+                if (lane == 31) {
+                    sm.warp_agg[b][warp] = inc | (warp_par << 31);
+                    if (warp == 0) sm.agg_tile[b] = tile;
+                    mbar_arrive(&sm.agg_full[b]);
+                }
+            } else if (lane == 31) {
+                if (warp == 0) sm.agg_tile[b] = kInvalidTile;
+                mbar_arrive(&sm.agg_full[b]);
+            }
+
+            // ---- ordered compaction of the tile classified kSkew iterations ago: its look-back has had
+            //      kSkew classify phases to complete ----
+            if (pend[0].tile != kInvalidTile) compact_tile(sm, p, pend[0], it - kSkew, tid, lane, warp);
+            if (tile == kInvalidTile) {
+                // drain: the younger pending tiles, oldest first
+#pragma unroll
+                for (int k = 1; k < kSkew; ++k)
+                    if (pend[k].tile != kInvalidTile) compact_tile(sm, p, pend[k], it - kSkew + k, tid, lane, warp);
+                break;
+            }
+#pragma unroll
+            for (int k = 0; k + 1 < kSkew; ++k) pend[k] = pend[k + 1];
+            pend[kSkew - 1] = cur;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+}  // namespace
+
+bool tma_path_usable(uint64_t n) { return n >= 4ull * kTileBytes && encode_tiled_fn() != nullptr; }
+
+cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream)
+{
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return cudaErrorNotSupported;
+    // 2-D view of the input: [rows = n / 128][128 bytes]; rows beyond the end read as zeros
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {128, (cuuint64_t)(p.n >> 7)};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {128, (cuuint32_t)kRowsPerTile};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(p.in), gdim, gstride, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    static int grid_cap = 0;
+    if (grid_cap == 0) {
+        cudaError_t e = cudaFuncSetAttribute(index_build_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(SmemTma));
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 148, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, index_build_tma_kernel, kTmaThreads, sizeof(SmemTma));
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        grid_cap = sms * per_sm;   // persistent: one resident CTA per slot (2 per SM by design)
+    }
+    const unsigned grid = (unsigned)(p.num_tiles < (uint32_t)grid_cap ? p.num_tiles : (uint32_t)grid_cap);
+    index_build_tma_kernel<<<grid, kTmaThreads, sizeof(SmemTma), stream>>>(p, tmap);
+    return cudaGetLastError();
+}
+
+}  // namespace csvb200

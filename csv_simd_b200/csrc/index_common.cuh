@@ -1,0 +1,146 @@
+// index_common.cuh -- device helpers shared by the two index-build kernels
+// (index_build.cu: simple one-tile-per-CTA kernel; index_build_tma.cu: persistent TMA pipeline).
+#pragma once
+#include "bitslice.cuh"
+#include "internal.h"
+
+namespace csvb200 {
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_stream_128(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_128(void* p, uint64_t a, uint64_t b)
+{
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+struct WarpState {
+    uint32_t par;   // quote parity of the warps before this one (relative to tile start)
+    uint32_t off0;  // entries emitted by those warps if the tile is entered outside quotes
+    uint32_t off1;  // ... if entered inside quotes
+};
+
+constexpr int kGroups = kBytesPerThread / 32;   // 32-byte bit-slice groups per thread
+constexpr int kChunks = kBytesPerThread / 16;   // 16-byte chunks per thread
+
+// Warp-parallel decoupled look-back over the monoid (p, c0, c1) (see index_build.cu header).
+// Called by one full warp after the tile's own aggregate has been published; returns the quote
+// parity entering the tile (pin) and the number of index entries emitted before it (base).
+//
+// kLookbackPerLane descriptors are inspected per lane and round trip, i.e. a window of
+// 32 * kLookbackPerLane predecessor tiles.  All resident CTAs advance in near lock-step, so the
+// nearest published prefix is typically one "wave" (= number of resident CTAs) of tiles back; a
+// window that covers the whole wave resolves the look-back in about one L2 round trip instead of
+// wave / 32 serial ones (ncu: >50 % of worker stalls were waits on this chain with a 64-tile window).
+template <int kLookbackPerLane>
+__device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_t tile, uint32_t lane, uint32_t& pin_out,
+                                                   uint64_t& base_out)
+{
+    // virtual predecessor of tile 0: the carry entering this launch (only tiles whose look-back
+    // window reaches below tile 0 ever evaluate it)
+    auto virtual_prefix = [&]() -> uint64_t {
+        uint64_t carry_count = p.carry_count;
+        uint32_t carry_parity = p.carry_parity;
+        if (p.carry != nullptr) {
+            carry_count = p.carry[0];
+            carry_parity = (uint32_t)p.carry[1] & 1u;
+        }
+        if (p.shard_par != nullptr) {
+            carry_parity = 0u;
+            for (uint32_t j = 0; j < p.shard_rank; ++j) carry_parity ^= p.shard_par[j] & 1u;
+        }
+        return kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
+    };
+
+    // Suffix composite S = (sp, sc0, sc1) of the tiles already absorbed (those nearest to us).
+    // One round inspects a window of 32 * kLookbackPerLane predecessors: lane L owns the
+    // kLookbackPerLane CONSECUTIVE tiles idx0 - L*kLookbackPerLane - j (j = 0 nearest) and folds
+    // them with plain register arithmetic (no warp collectives); one set of ballots / reductions
+    // then combines the 32 lane composites.  All loads of a round are in flight together.
+    uint32_t sp = 0u;
+    uint64_t sc0 = 0ull, sc1 = 0ull;
+    int64_t idx0 = (int64_t)tile - 1;
+    uint32_t pin = 0u;
+    uint64_t base = 0ull;
+    while (true) {
+        uint64_t d[kLookbackPerLane];
+#pragma unroll
+        for (int j = 0; j < kLookbackPerLane; ++j) {
+            const int64_t idx = idx0 - (int64_t)lane * kLookbackPerLane - j;
+            d[j] = idx >= 0 ? ld_relaxed_u64(p.desc + idx * kDescStride) : virtual_prefix();
+        }
+        // lane-local fold, nearest tile first: L <- agg(t_j) o L
+        uint32_t lp_ = 0u, l0 = 0u, l1 = 0u;   // lane composite (parity, c0, c1)
+        uint32_t stop = 0u;                    // 0 = all aggregates, 1 = met an unpublished tile, 2 = met a prefix
+        uint64_t pd = 0ull;                    // the prefix descriptor, if met
+#pragma unroll
+        for (int j = 0; j < kLookbackPerLane; ++j) {
+            const uint32_t status = (uint32_t)(d[j] >> 62);
+            if (stop == 0u) {
+                if (status == 1u) {
+                    const uint32_t ap = (uint32_t)((d[j] >> 61) & 1ull);
+                    const uint32_t a0 = (uint32_t)(d[j] & 0xfffffull), a1 = (uint32_t)((d[j] >> 20) & 0xfffffull);
+                    const uint32_t n0 = a0 + (ap ? l1 : l0);
+                    const uint32_t n1 = a1 + (ap ? l0 : l1);
+                    l0 = n0;
+                    l1 = n1;
+                    lp_ ^= ap;
+                } else {
+                    stop = status == 2u ? 2u : 1u;
+                    pd = d[j];
+                }
+            }
+        }
+        const uint32_t stopped = __ballot_sync(0xffffffffu, stop != 0u);
+        const uint32_t ls = stopped ? (uint32_t)(__ffs(stopped) - 1) : 32u;   // nearest lane that stopped
+        const uint32_t ls_stop = __shfl_sync(0xffffffffu, stop, (int)(ls & 31u));
+        if (ls < 32u && ls_stop == 1u) {   // an unpublished tile lies before the nearest prefix: poll again
+            __nanosleep(64);
+            continue;
+        }
+        // lanes 0..ls contribute (lane ls only the tiles nearer than its prefix)
+        const bool in_win = lane <= ls;
+        const uint32_t pj = in_win ? lp_ : 0u;
+        const uint32_t bp = __ballot_sync(0xffffffffu, pj != 0u);
+        // parity accumulated by the window tiles EARLIER than this lane's (= higher lanes)
+        const uint32_t rel = __popc(bp & (0xfffffffeu << lane)) & 1u;
+        const uint32_t w0j = in_win ? (rel ? l1 : l0) : 0u;
+        const uint32_t w1j = in_win ? (rel ? l0 : l1) : 0u;
+        const uint32_t W0 = __reduce_add_sync(0xffffffffu, w0j);
+        const uint32_t W1 = __reduce_add_sync(0xffffffffu, w1j);
+        const uint32_t Wp = __popc(bp) & 1u;
+        // S <- W o S   (the window is earlier in the file than everything absorbed so far)
+        const uint64_t n0 = (uint64_t)W0 + (Wp ? sc1 : sc0);
+        const uint64_t n1 = (uint64_t)W1 + (Wp ? sc0 : sc1);
+        sc0 = n0;
+        sc1 = n1;
+        sp ^= Wp;
+        if (ls < 32u) {
+            const uint64_t pref = __shfl_sync(0xffffffffu, pd, (int)ls);
+            const uint32_t P = (uint32_t)((pref >> 61) & 1ull);
+            pin = P ^ sp;
+            base = (pref & kCountMask) + (P ? sc1 : sc0);
+            break;
+        }
+        idx0 -= 32 * kLookbackPerLane;
+    }
+    pin_out = pin;
+    base_out = base;
+}
+
+}  // namespace csvb200

@@ -18,6 +18,11 @@ constexpr int kWarps = kThreads / 32;
 //   aggregate: [19:0] c0 = unquoted separators if the tile is entered outside quotes
 //              [39:20] c1 = same if entered inside quotes
 //   prefix:    [60:0] absolute number of index entries emitted up to the tile end
+// Each descriptor sits alone in a 128-byte line: every resident CTA polls the descriptors of the
+// same few hundred predecessor tiles, and packed (8-byte stride) descriptors put all of that
+// traffic on a handful of L2 slices (measured: 5x slower with a 320-tile window).  One line per
+// descriptor spreads the polls over all slices through the address hash.
+constexpr uint64_t kDescStride = 16;  // in u64 words
 constexpr uint64_t kStatusAgg = 1ull << 62;
 constexpr uint64_t kStatusPrefix = 2ull << 62;
 constexpr uint64_t kParityBit = 1ull << 61;
@@ -42,9 +47,14 @@ struct BuildParams {
     // this shard is the XOR of shard_par[0 .. shard_rank) (overrides carry_parity when non-null)
     const uint32_t* shard_par;
     uint32_t shard_rank;
+    uint32_t tune;           // experiment knob (CSVB200_TUNE)
 };
 
+// one tile per CTA, plain loads: small inputs and cross-check of the TMA kernel
 cudaError_t launch_index_build(const BuildParams& p, cudaStream_t stream);
+// persistent warp-specialised TMA pipeline (index_build_tma.cu): the production path for large inputs
+cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream);
+bool tma_path_usable(uint64_t n);
 
 // quote parity of a byte range (pass A of the multi-GPU protocol); *out ^= parity
 cudaError_t launch_quote_parity(const uint8_t* in, uint64_t n, uint32_t* out, cudaStream_t stream);

@@ -305,3 +305,56 @@ def test_full_size_properties(ctx, kind):
     assert total == E and csum == checksum
     idx.free()
     idx2.free()
+
+
+# ---- the two CUDA kernels (one-tile-per-CTA and the persistent TMA pipeline) against each other and the oracle ----
+@pytest.fixture(scope="module")
+def forced_ctxs():
+    out = {}
+    for k in ("simple", "tma"):
+        os.environ["CSVB200_KERNEL"] = k
+        out[k] = cs.Context(0)
+    os.environ.pop("CSVB200_KERNEL", None)
+    yield out
+    for c in out.values():
+        c.close()
+
+
+@pytest.mark.parametrize("name,data", [c for c in cases.edge_cases() if len(c[1]) >= 128],
+                         ids=[c[0] for c in cases.edge_cases() if len(c[1]) >= 128])
+def test_both_kernels_edge_cases(forced_ctxs, name, data):
+    want = O.read_sse(data)
+    for k, c in forced_ctxs.items():
+        got, par = build(c, data)
+        assert got.shape == want.shape and (got == want).all(), k
+        assert par == (data.count(b'"') & 1), k
+
+
+def test_both_kernels_fuzz_multi_tile(forced_ctxs):
+    for seed in range(40):
+        n = 128 + (seed * 104729) % (40 * cases.TILE)
+        data = cases.rand_bytes(n, 1000 + seed) if seed % 5 else cases.full_random(n, seed)
+        want = O.read_sse(data)
+        for k, c in forced_ctxs.items():
+            got, _ = build(c, data)
+            assert got.shape == want.shape and (got == want).all(), (k, seed, n)
+
+
+def test_tma_kernel_dense_rounds_and_shards(forced_ctxs):
+    c = forced_ctxs["tma"]
+    # one entry per byte: every tile needs 4 staging rounds
+    data = b"," * (5 * cases.TILE + 77)
+    got, _ = build(c, data)
+    assert got.size == len(data) + 1 and (got[1:] == np.arange(len(data), dtype=np.uint64)).all()
+    data = (b'",' * (3 * cases.TILE))[: 5 * cases.TILE + 1]
+    want = O.read_sse(data)
+    got, _ = build(c, data)
+    assert (got == want).all()
+    # shard chain (carry-in parity, global offsets, odd output bases) through the TMA kernel
+    q, _ = gen.quoted(2 << 20, seed=44)
+    raw = q.tobytes()
+    want = O.closed_form_numpy(raw)
+    n = len(raw)
+    cuts = [0] + [(k * n) // 3 + 37 * k + 13 for k in range(1, 3)] + [n]
+    got, _ = _shard_chain(c, raw, cuts)
+    assert (got == want).all()
