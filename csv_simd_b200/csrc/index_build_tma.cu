@@ -2,20 +2,24 @@
 //
 // Same algorithm and output as index_build.cu (see its header for the reference mapping:
 // reader::read src/reader.rs:150-306, SimdInput::structure src/avx/stage1.rs:193-407,
-// Stage1::crush_set_bits src/stage1.rs:162-296), re-organised around what bounds it on B200:
+// Stage1::crush_set_bits src/stage1.rs:162-296), re-organised around what bounds it on B200
+// (every step below is backed by an ncu capture, see profiles/ and DESIGN.md):
 //
-//   * ncu on the one-tile-per-CTA kernel showed >50 % of warp stalls at the barrier behind the
-//     decoupled look-back and a load stage that needs registers + LSU slots.  Here the CTA is
-//     persistent (2 per SM) and split into roles:
-//       warps 0-7  workers : classify / scan / compact            (256 threads x 128 B = 32 KiB tile)
-//       warp  8    producer: takes tile tickets, issues one TMA 2-D tile load per tile
+//   * the CTA is persistent (2 per SM) and split into roles:
+//       warps 0-7  workers : classify / scan / compact      (256 threads x 128 B = one 32 KiB sub-tile)
+//       warp  8    producer: takes tickets, issues one TMA 2-D load per sub-tile
 //                            (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier complete_tx)
-//       warp  9    look-back: scans the 8 warp aggregates, publishes the tile descriptor, runs the
+//       warp  9    look-back: scans the warp aggregates, publishes the descriptor, runs the
 //                            warp-parallel decoupled look-back, hands (parity, base) to the workers
-//   * the compaction of tile k is skewed behind the classification of tile k+1, so the look-back
-//     latency (a few L2 round trips) is covered by useful work instead of a barrier stall;
-//   * the input is a 2-D tensor map [rows = n/128][128 B]; rows past the end are zero-filled by
-//     the TMA unit, which reproduces the reference's zero padding of the last block
+//   * a look-back descriptor covers a SUPER-TILE of kSub consecutive sub-tiles (64 KiB): the chain of
+//     prefixes advances one 32-descriptor window per L2 round trip, so bytes per descriptor set the
+//     chain's byte rate; with one descriptor per 32 KiB the kernel was chain-bound at ~2.4 TB/s;
+//   * the compaction of super-tile k is skewed behind the classification of super-tile k+1, so the
+//     look-back latency is covered by useful work instead of a barrier stall;
+//   * every descriptor sits in its own 128-byte line (internal.h kDescStride): hundreds of CTAs poll
+//     the same few hundred descriptors and packed descriptors serialise on a handful of L2 slices;
+//   * the input is a 2-D tensor map [rows = n/128][128 B]; rows past the end are zero-filled by the
+//     TMA unit, which reproduces the reference's zero padding of the last block
 //     (src/avx/stage1.rs:54-88) for free; the sub-row tail (< 128 B) is patched in by one thread.
 #include <cuda.h>
 
@@ -29,32 +33,32 @@ constexpr int kWorkerWarps = kWarps;             // 8
 constexpr int kProducerWarp = kWorkerWarps;      // warp 8
 constexpr int kLookbackWarp = kWorkerWarps + 1;  // warp 9
 constexpr int kTmaThreads = kThreads + 64;       // 320
-constexpr int kStages = 2;                       // TMA ring depth (x 2 CTAs/SM = 128 KiB in flight per SM)
-constexpr int kStageCap = 8192;                  // entries per staging buffer; denser tiles take extra rounds
+constexpr int kSub = 2;                          // sub-tiles (TMA boxes) per look-back descriptor
+constexpr int kSuperBytes = kSub * kTileBytes;   // 64 KiB per descriptor
+constexpr int kStages = 2;                       // TMA ring depth in sub-tiles (x 2 CTAs/SM = 128 KiB in flight per SM)
+constexpr int kStageCap = 8192;                  // entries per staging buffer; denser sub-tiles take extra rounds
 constexpr int kRowsPerTile = kTileBytes / 128;   // 256 = max TMA box extent
-constexpr int kSkew = 2;                         // tiles classified ahead of the tile being compacted
+constexpr int kSkew = 1;                         // super-tiles classified ahead of the one being compacted
 constexpr int kRing = kSkew + 1;                 // ring depth of the worker <-> look-back hand-off buffers
 constexpr uint32_t kInvalidTile = 0xffffffffu;
 
 struct PrefixInfo {
-    uint32_t pin;    // quote parity entering the tile
-    uint32_t tot0;   // entries of the tile if entered outside quotes
-    uint32_t tot1;   // ... inside quotes
-    uint32_t pad;
-    uint64_t base;   // entries emitted before the tile
-    WarpState ws[kWorkerWarps];
+    uint32_t pin[kSub];    // quote parity entering each sub-tile
+    uint32_t cnt[kSub];    // entries each sub-tile emits (under its actual entry parity)
+    uint64_t base[kSub];   // entries emitted before each sub-tile
+    WarpState ws[kSub][kWorkerWarps];
 };
 
 struct __align__(1024) SmemTma {
     uint8_t in[kStages][kTileBytes];        // TMA destinations, 1024-byte aligned (SWIZZLE_128B)
-    uint16_t stage[2][kStageCap + 8];       // 16-bit tile-relative offsets, double buffered by tile parity
+    uint16_t stage[2][kStageCap + 8];       // 16-bit sub-tile-relative offsets, double buffered
     uint64_t full[kStages];                 // producer -> workers (TMA complete_tx)
     uint64_t empty[kStages];                // workers -> producer
     uint64_t agg_full[kRing];               // workers -> look-back warp
     uint64_t pref_full[kRing];              // look-back warp -> workers
-    uint32_t tile_id[kStages];
+    uint32_t tile_id[kStages];              // super-tile id of the sub-tile in each stage
     uint32_t agg_tile[kRing];
-    uint32_t warp_agg[kRing][kWorkerWarps];
+    uint32_t warp_agg[kRing][kSub][kWorkerWarps];
     PrefixInfo pref[kRing];
 };
 
@@ -72,6 +76,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the warp in hardware up to the time hint instead of burning issue slots
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
@@ -79,10 +84,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(2000u)
             : "memory");
     } while (!ok);
 }
@@ -97,7 +102,7 @@ __device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap*
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
 // streams staged entries [j0, j1) (staging indices, j0 even) of a run whose staging index 0 maps to
-// global slot `out`; positions are tile_pos + 16-bit offset
+// global slot gbase; positions are tile_pos + 16-bit offset
 __device__ __forceinline__ void copy_out_range(const BuildParams& p, const uint16_t* stg, uint32_t local0, uint32_t j0,
                                                uint32_t j1, uint64_t gbase, uint64_t tile_pos, uint32_t tid)
 {
@@ -115,37 +120,36 @@ __device__ __forceinline__ void copy_out_range(const BuildParams& p, const uint1
     }
 }
 
-// per-thread state of a classified tile awaiting compaction
+// per-thread state of a classified sub-tile awaiting compaction
 struct TileRegs {
     uint32_t s[kGroups];   // separator masks
     uint32_t x[kGroups];   // in-string masks relative to the warp start
     uint32_t exc;          // packed exclusive warp scan: entries before this thread (outside-hypothesis | total << 16)
-    uint32_t tile;
+};
+struct SuperRegs {
+    TileRegs sub[kSub];
+    uint32_t tile;         // super-tile id
 };
 
-// Ordered compaction of one tile (the `it`-th tile this CTA processed): wait for its (parity, base)
-// from the look-back warp, expand the masks into 16-bit offsets in shared memory at the scanned
-// slots, then stream the run out as 16-byte stores.
-__device__ __forceinline__ void compact_tile(SmemTma& sm, const BuildParams& p, const TileRegs& t, uint32_t it, uint32_t tid,
-                                             uint32_t lane, uint32_t warp)
+// Ordered compaction of one sub-tile: expand the masks into 16-bit offsets in shared memory at the
+// scanned slots, then stream the run out as 16-byte stores.  `seq` numbers the sub-tile compactions
+// of this CTA (it alternates the staging buffer).
+__device__ __forceinline__ void compact_sub(SmemTma& sm, const BuildParams& p, const TileRegs& t, const PrefixInfo& pi,
+                                            int sub, uint32_t super_tile, uint32_t seq, uint32_t tid, uint32_t warp)
 {
-    (void)lane;
-    const uint32_t pb = it % kRing;
-    mbar_wait(&sm.pref_full[pb], (it / kRing) & 1u);
-    const PrefixInfo& pi = sm.pref[pb];
-    const uint32_t pin = pi.pin;
-    const uint32_t cnt = pin ? pi.tot1 : pi.tot0;
-    const uint64_t g0 = p.out_base + pi.base;       // slot of the tile's first entry
-    const uint32_t head = (uint32_t)(g0 & 1ull);     // keep even slots on even staging indices
+    const uint32_t pin = pi.pin[sub];
+    const uint32_t cnt = pi.cnt[sub];
+    const uint64_t g0 = p.out_base + pi.base[sub];   // slot of the sub-tile's first entry
+    const uint32_t head = (uint32_t)(g0 & 1ull);      // keep even slots on even staging indices
     const uint32_t end = cnt + head;
     const uint64_t gbase = g0 - head;
-    const uint64_t tile_pos = p.pos_bias + (uint64_t)t.tile * kTileBytes;
-    const WarpState ws = pi.ws[warp];
-    const uint32_t h = pin ^ ws.par;                 // parity entering this warp
+    const uint64_t tile_pos = p.pos_bias + (uint64_t)super_tile * kSuperBytes + (uint64_t)sub * kTileBytes;
+    const WarpState ws = pi.ws[sub][warp];
+    const uint32_t h = pin ^ ws.par;                  // parity entering this warp
     const uint32_t ex_a0 = t.exc & 0xffffu, ex_tt = t.exc >> 16;
     const uint32_t slot0 = head + (pin ? ws.off1 : ws.off0) + (h ? ex_tt - ex_a0 : ex_a0);
     const uint32_t flip = 0u - h;
-    uint16_t* stg = sm.stage[it & 1u];
+    uint16_t* stg = sm.stage[seq & 1u];
     if (end <= (uint32_t)kStageCap) {
         uint16_t* dst = stg + slot0;
 #pragma unroll
@@ -163,7 +167,7 @@ __device__ __forceinline__ void compact_tile(SmemTma& sm, const BuildParams& p, 
         // no trailing barrier: this staging buffer is next written two compactions from now,
         // behind the other buffer's worker_barrier()
     } else {
-        // dense tile (more than kStageCap entries): several staging rounds
+        // dense sub-tile (more than kStageCap entries): several staging rounds
         for (uint32_t r0 = 0; r0 < end; r0 += (uint32_t)kStageCap) {
             uint32_t slot = slot0;
 #pragma unroll
@@ -183,6 +187,17 @@ __device__ __forceinline__ void compact_tile(SmemTma& sm, const BuildParams& p, 
             worker_barrier();
         }
     }
+}
+
+// compaction of the `it`-th super-tile this CTA processed
+__device__ __forceinline__ void compact_super(SmemTma& sm, const BuildParams& p, const SuperRegs& t, uint32_t it,
+                                              uint32_t tid, uint32_t warp)
+{
+    const uint32_t pb = it % kRing;
+    mbar_wait(&sm.pref_full[pb], (it / kRing) & 1u);
+    const PrefixInfo& pi = sm.pref[pb];
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) compact_sub(sm, p, t.sub[sub], pi, sub, t.tile, it * kSub + sub, tid, warp);
 }
 
 __global__ void __launch_bounds__(kTmaThreads, 2)
@@ -214,18 +229,23 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
             for (uint32_t it = 0;; ++it) {
-                const uint32_t st = it % kStages;
-                mbar_wait(&sm.empty[st], ((it / kStages) & 1u) ^ 1u);
-                // dynamic tile id: a tile only ever waits on tiles whose CTAs already hold a ticket
-                const uint32_t tile = atomicAdd(p.ticket, 1u);
-                if (tile >= p.num_tiles) {
-                    sm.tile_id[st] = kInvalidTile;
-                    mbar_arrive(&sm.full[st]);
-                    break;
+                // dynamic super-tile id: a tile only ever waits on tiles whose CTAs already hold a ticket
+                uint32_t tile = atomicAdd(p.ticket, 1u);
+                if (tile >= p.num_tiles) tile = kInvalidTile;
+#pragma unroll
+                for (int sub = 0; sub < kSub; ++sub) {
+                    const uint32_t sc = it * kSub + sub, st = sc % kStages;
+                    mbar_wait(&sm.empty[st], ((sc / kStages) & 1u) ^ 1u);
+                    sm.tile_id[st] = tile;
+                    if (tile == kInvalidTile) {
+                        mbar_arrive(&sm.full[st]);
+                        break;
+                    }
+                    mbar_arrive_expect_tx(&sm.full[st], (uint32_t)kTileBytes);
+                    tma_load_tile(sm.in[st], &tmap, 0, (int32_t)((tile * (uint32_t)kSub + sub) * (uint32_t)kRowsPerTile),
+                                  &sm.full[st]);
                 }
-                sm.tile_id[st] = tile;
-                mbar_arrive_expect_tx(&sm.full[st], (uint32_t)kTileBytes);
-                tma_load_tile(sm.in[st], &tmap, 0, (int32_t)(tile * (uint32_t)kRowsPerTile), &sm.full[st]);
+                if (tile == kInvalidTile) break;
             }
         }
     } else if (warp == kLookbackWarp) {
@@ -235,38 +255,54 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             mbar_wait(&sm.agg_full[b], (it / kRing) & 1u);
             const uint32_t tile = sm.agg_tile[b];
             if (tile == kInvalidTile) break;
+            PrefixInfo& pi = sm.pref[b];
+            // fold the kSub x 8 warp aggregates in file order; remember the state entering every warp
+            // and the (parity, c0, c1) composite at every sub-tile boundary
             uint32_t par = 0u, o0 = 0u, o1 = 0u;
+            uint32_t sub_par[kSub], sub_o0[kSub], sub_o1[kSub];
 #pragma unroll
-            for (int w = 0; w < kWorkerWarps; ++w) {
-                const uint32_t v = sm.warp_agg[b][w];
-                const uint32_t wa0 = v & 0x7fffu, wt = (v >> 16) & 0x7fffu, wa1 = wt - wa0;
-                if (lane == 0) {
-                    sm.pref[b].ws[w].par = par;
-                    sm.pref[b].ws[w].off0 = o0;
-                    sm.pref[b].ws[w].off1 = o1;
+            for (int sub = 0; sub < kSub; ++sub) {
+                sub_par[sub] = par;
+                sub_o0[sub] = o0;
+                sub_o1[sub] = o1;
+#pragma unroll
+                for (int w = 0; w < kWorkerWarps; ++w) {
+                    const uint32_t v = sm.warp_agg[b][sub][w];
+                    const uint32_t wa0 = v & 0x7fffu, wt = (v >> 16) & 0x7fffu, wa1 = wt - wa0;
+                    if (lane == 0) {
+                        // warp state relative to the start of ITS sub-tile
+                        pi.ws[sub][w].par = par ^ sub_par[sub];
+                        pi.ws[sub][w].off0 = (sub_par[sub] ? o1 : o0) - (sub_par[sub] ? sub_o1[sub] : sub_o0[sub]);
+                        pi.ws[sub][w].off1 = (sub_par[sub] ? o0 : o1) - (sub_par[sub] ? sub_o0[sub] : sub_o1[sub]);
+                    }
+                    o0 += par ? wa1 : wa0;
+                    o1 += par ? wa0 : wa1;
+                    par ^= v >> 31;
                 }
-                o0 += par ? wa1 : wa0;
-                o1 += par ? wa0 : wa1;
-                par ^= v >> 31;
             }
             if (lane == 0)
                 st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride,
                                kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
             uint32_t pin;
             uint64_t base;
-            switch (p.tune) {
-            case 2: decoupled_lookback<2>(p, tile, lane, pin, base); break;
-            case 4: decoupled_lookback<4>(p, tile, lane, pin, base); break;
-            default: decoupled_lookback<1>(p, tile, lane, pin, base); break;  // measured best: 0.45 / 0.48 / 0.59 ms for 1 / 2 / 4
-            }
+            if (p.tune == 2)
+                decoupled_lookback<2>(p, tile, lane, pin, base);
+            else
+                decoupled_lookback<1>(p, tile, lane, pin, base);   // measured best: 0.45 / 0.48 / 0.59 ms for 1 / 2 / 4
             if (lane == 0) {
                 const uint32_t pend = pin ^ par;
                 const uint64_t cend = base + (pin ? o1 : o0);
-                st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride, kStatusPrefix | (pend ? kParityBit : 0ull) | (cend & kCountMask));
-                sm.pref[b].pin = pin;
-                sm.pref[b].base = base;
-                sm.pref[b].tot0 = o0;
-                sm.pref[b].tot1 = o1;
+                st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride,
+                               kStatusPrefix | (pend ? kParityBit : 0ull) | (cend & kCountMask));
+#pragma unroll
+                for (int sub = 0; sub < kSub; ++sub) {
+                    const uint64_t b0 = base + (pin ? sub_o1[sub] : sub_o0[sub]);
+                    const uint64_t b1 = sub + 1 < kSub ? base + (pin ? sub_o1[sub + 1 < kSub ? sub + 1 : sub] : sub_o0[sub + 1 < kSub ? sub + 1 : sub])
+                                                       : cend;
+                    pi.pin[sub] = pin ^ sub_par[sub];
+                    pi.base[sub] = b0;
+                    pi.cnt[sub] = (uint32_t)(b1 - b0);
+                }
                 if (tile == p.num_tiles - 1) {
                     p.result[0] = cend;
                     p.result[1] = pend;
@@ -283,25 +319,31 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
         // ===== workers =====
         const uint64_t full_rows = p.n >> 7;
         const uint32_t tail = (uint32_t)(p.n & 127u);
-        // masks of the tiles that are classified but not yet compacted (kSkew of them, oldest first)
-        TileRegs pend[kSkew];
+        // masks of the super-tiles that are classified but not yet compacted (kSkew of them, oldest first)
+        SuperRegs pend[kSkew];
 #pragma unroll
         for (int k = 0; k < kSkew; ++k) pend[k].tile = kInvalidTile;
 
         for (uint32_t it = 0;; ++it) {
-            const uint32_t st = it % kStages, b = it % kRing;
-            mbar_wait(&sm.full[st], (it / kStages) & 1u);
-            const uint32_t tile = sm.tile_id[st];
-            TileRegs cur;
-            cur.tile = tile;
-            cur.exc = 0u;
+            const uint32_t b = it % kRing;
+            SuperRegs cur;
+            cur.tile = kInvalidTile;
 #pragma unroll
-            for (int g = 0; g < kGroups; ++g) cur.s[g] = cur.x[g] = 0u;
+            for (int sub = 0; sub < kSub; ++sub) {
+                TileRegs& tr = cur.sub[sub];
+                tr.exc = 0u;
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) tr.s[g] = tr.x[g] = 0u;
+                if (sub > 0 && cur.tile == kInvalidTile) continue;   // the producer stops after an invalid sub-tile 0
+                const uint32_t sc = it * kSub + sub, st = sc % kStages;
+                mbar_wait(&sm.full[st], (sc / kStages) & 1u);
+                const uint32_t tile = sm.tile_id[st];
+                cur.tile = tile;
+                if (tile == kInvalidTile) continue;
 
-            if (tile != kInvalidTile) {
                 uint8_t* in = sm.in[st];
                 // the sub-row tail of the file is outside the tensor map: its owner patches it in
-                if (tail != 0u && (uint64_t)tile * kRowsPerTile + tid == full_rows) {
+                if (tail != 0u && ((uint64_t)tile * kSub + sub) * kRowsPerTile + tid == full_rows) {
                     for (uint32_t k = 0; k < tail; ++k) {
                         const uint32_t c = (uint32_t)kChunks * tid + (k >> 4);
                         in[16u * (c ^ ((c >> 3) & 7u)) + (k & 15u)] = p.in[full_rows * 128u + k];
@@ -323,7 +365,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                     }
                     const Masks32 m = classify32(w);
                     q[g] = m.quote;
-                    cur.s[g] = m.sep;
+                    tr.s[g] = m.sep;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty[st]);  // stage can be refilled
@@ -336,21 +378,21 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                     uint32_t carry = 0u;
 #pragma unroll
                     for (int g = 0; g < kGroups; ++g) {
-                        cur.x[g] = prefix_xor32(q[g]) ^ carry;
-                        carry = 0u - (cur.x[g] >> 31);
+                        tr.x[g] = prefix_xor32(q[g]) ^ carry;
+                        carry = 0u - (tr.x[g] >> 31);
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, carry != 0u);
                     const uint32_t lane_in = __popc(bal & ((1u << lane) - 1u)) & 1u;
                     warp_par = __popc(bal) & 1u;
                     const uint32_t flip = 0u - lane_in;
 #pragma unroll
-                    for (int g = 0; g < kGroups; ++g) cur.x[g] ^= flip;
+                    for (int g = 0; g < kGroups; ++g) tr.x[g] ^= flip;
                 }
                 uint32_t a0 = 0u, tt = 0u;
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
-                    a0 += __popc(cur.s[g] & ~cur.x[g]);
-                    tt += __popc(cur.s[g]);
+                    a0 += __popc(tr.s[g] & ~tr.x[g]);
+                    tt += __popc(tr.s[g]);
                 }
                 const uint32_t packed = a0 | (tt << 16);
                 uint32_t inc = packed;
@@ -359,25 +401,22 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                     const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
                     if (lane >= (uint32_t)d) inc += v;
                 }
-                cur.exc = inc - packed;
-                if (lane == 31) {
-                    sm.warp_agg[b][warp] = inc | (warp_par << 31);
-                    if (warp == 0) sm.agg_tile[b] = tile;
-                    mbar_arrive(&sm.agg_full[b]);
-                }
-            } else if (lane == 31) {
-                if (warp == 0) sm.agg_tile[b] = kInvalidTile;
+                tr.exc = inc - packed;
+                if (lane == 31) sm.warp_agg[b][sub][warp] = inc | (warp_par << 31);
+            }
+            if (lane == 31) {
+                if (warp == 0) sm.agg_tile[b] = cur.tile;
                 mbar_arrive(&sm.agg_full[b]);
             }
 
-            // ---- ordered compaction of the tile classified kSkew iterations ago: its look-back has had
-            //      kSkew classify phases to complete ----
-            if (pend[0].tile != kInvalidTile) compact_tile(sm, p, pend[0], it - kSkew, tid, lane, warp);
-            if (tile == kInvalidTile) {
-                // drain: the younger pending tiles, oldest first
+            // ---- ordered compaction of the super-tile classified kSkew iterations ago: its look-back has
+            //      had kSkew classify phases to complete ----
+            if (pend[0].tile != kInvalidTile) compact_super(sm, p, pend[0], it - kSkew, tid, warp);
+            if (cur.tile == kInvalidTile) {
+                // drain: the younger pending super-tiles, oldest first
 #pragma unroll
                 for (int k = 1; k < kSkew; ++k)
-                    if (pend[k].tile != kInvalidTile) compact_tile(sm, p, pend[k], it - kSkew + k, tid, lane, warp);
+                    if (pend[k].tile != kInvalidTile) compact_super(sm, p, pend[k], it - kSkew + k, tid, warp);
                 break;
             }
 #pragma unroll
@@ -406,10 +445,13 @@ EncodeTiledFn encode_tiled_fn()
 
 }  // namespace
 
-bool tma_path_usable(uint64_t n) { return n >= 4ull * kTileBytes && encode_tiled_fn() != nullptr; }
+bool tma_path_usable(uint64_t n) { return n >= 4ull * kSuperBytes && encode_tiled_fn() != nullptr; }
 
-cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream)
+cudaError_t launch_index_build_tma(const BuildParams& p_in, cudaStream_t stream)
 {
+    BuildParams p = p_in;
+    p.num_tiles = (uint32_t)((p.n + kSuperBytes - 1) / kSuperBytes);   // descriptors are per super-tile here
+    if (p.num_tiles == 0) p.num_tiles = 1;
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return cudaErrorNotSupported;
     // 2-D view of the input: [rows = n / 128][128 bytes]; rows beyond the end read as zeros
@@ -435,7 +477,8 @@ cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream)
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         grid_cap = sms * per_sm;   // persistent: one resident CTA per slot (2 per SM by design)
     }
-    const unsigned grid = (unsigned)(p.num_tiles < (uint32_t)grid_cap ? p.num_tiles : (uint32_t)grid_cap);
+    unsigned grid = (unsigned)(p.num_tiles < (uint32_t)grid_cap ? p.num_tiles : (uint32_t)grid_cap);
+    if (p.tune >= 8u && grid < 2u) grid = 2u;   // scanner mode: CTA 0 scans, the others take tiles
     index_build_tma_kernel<<<grid, kTmaThreads, sizeof(SmemTma), stream>>>(p, tmap);
     return cudaGetLastError();
 }

@@ -38,6 +38,22 @@ struct WarpState {
 constexpr int kGroups = kBytesPerThread / 32;   // 32-byte bit-slice groups per thread
 constexpr int kChunks = kBytesPerThread / 16;   // 16-byte chunks per thread
 
+// Virtual predecessor of tile 0: the carry entering this launch, encoded as a prefix descriptor.
+__device__ __forceinline__ uint64_t virtual_prefix_desc(const BuildParams& p)
+{
+    uint64_t carry_count = p.carry_count;
+    uint32_t carry_parity = p.carry_parity;
+    if (p.carry != nullptr) {
+        carry_count = p.carry[0];
+        carry_parity = (uint32_t)p.carry[1] & 1u;
+    }
+    if (p.shard_par != nullptr) {
+        carry_parity = 0u;
+        for (uint32_t j = 0; j < p.shard_rank; ++j) carry_parity ^= p.shard_par[j] & 1u;
+    }
+    return kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
+}
+
 // Warp-parallel decoupled look-back over the monoid (p, c0, c1) (see index_build.cu header).
 // Called by one full warp after the tile's own aggregate has been published; returns the quote
 // parity entering the tile (pin) and the number of index entries emitted before it (base).
@@ -51,21 +67,7 @@ template <int kLookbackPerLane>
 __device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_t tile, uint32_t lane, uint32_t& pin_out,
                                                    uint64_t& base_out)
 {
-    // virtual predecessor of tile 0: the carry entering this launch (only tiles whose look-back
-    // window reaches below tile 0 ever evaluate it)
-    auto virtual_prefix = [&]() -> uint64_t {
-        uint64_t carry_count = p.carry_count;
-        uint32_t carry_parity = p.carry_parity;
-        if (p.carry != nullptr) {
-            carry_count = p.carry[0];
-            carry_parity = (uint32_t)p.carry[1] & 1u;
-        }
-        if (p.shard_par != nullptr) {
-            carry_parity = 0u;
-            for (uint32_t j = 0; j < p.shard_rank; ++j) carry_parity ^= p.shard_par[j] & 1u;
-        }
-        return kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
-    };
+    auto virtual_prefix = [&]() -> uint64_t { return virtual_prefix_desc(p); };
 
     // Suffix composite S = (sp, sc0, sc1) of the tiles already absorbed (those nearest to us).
     // One round inspects a window of 32 * kLookbackPerLane predecessors: lane L owns the

@@ -58,7 +58,8 @@ def edge_cases():
     b[64] = 0x0A
     out.append(("crlf_across_block", bytes(b)))
     # tile-boundary cases for the CUDA kernel (16 KiB tiles)
-    for n in (TILE - 1, TILE, TILE + 1, 2 * TILE - 1, 2 * TILE, 2 * TILE + 17, 5 * TILE + 3):
+    for n in (TILE - 1, TILE, TILE + 1, 2 * TILE - 1, 2 * TILE, 2 * TILE + 17, 5 * TILE + 3, 8 * TILE, 9 * TILE + 129,
+              12 * TILE - 1):
         out.append((f"tile_rand_{n}", rand_bytes(n, 7 * n)))
     for qpos in (TILE - 1, TILE, TILE + 1):
         b = bytearray(b"ab,cd\n" * ((3 * TILE) // 6))
