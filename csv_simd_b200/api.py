@@ -61,7 +61,14 @@ class Context:
         self.close()
 
     def set_stream(self, cuda_stream: int | None):
-        self._check(self._lib.csvb200_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Bind the context to an external cudaStream_t handle.  None restores the private stream;
+        0 (what torch reports for its default stream) is mapped to cudaStreamLegacy (0x1), because a
+        NULL handle means "restore the private stream" in the C ABI."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = 1 if int(cuda_stream) == 0 else int(cuda_stream)
+        self._check(self._lib.csvb200_ctx_set_stream(self._h, C.c_void_p(handle)))
 
     def set_reserve(self, num: int, den: int):
         self._check(self._lib.csvb200_ctx_set_reserve(self._h, num, den))

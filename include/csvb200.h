@@ -69,7 +69,8 @@ int csvb200_ctx_create(int device, csvb200_ctx** out);
 void csvb200_ctx_destroy(csvb200_ctx* ctx);
 const char* csvb200_last_error(const csvb200_ctx* ctx);
 /* Run all work of this context on an externally owned cudaStream_t (e.g. the caller's current
- * stream, so the caller's CUDA events bracket the kernels).  NULL restores the private stream. */
+ * stream, so the caller's CUDA events bracket the kernels).  NULL restores the private stream;
+ * pass cudaStreamLegacy ((cudaStream_t)0x1) to run on the legacy default stream. */
 int csvb200_ctx_set_stream(csvb200_ctx* ctx, void* cuda_stream);
 /* Initial index capacity = n / ratio_den * ratio_num + 4096 entries (default 1/3); an index that
  * overflows it is transparently rebuilt with the exact size. */

@@ -358,3 +358,43 @@ def test_tma_kernel_dense_rounds_and_shards(forced_ctxs):
     cuts = [0] + [(k * n) // 3 + 37 * k + 13 for k in range(1, 3)] + [n]
     got, _ = _shard_chain(c, raw, cuts)
     assert (got == want).all()
+
+
+def test_stream_ordered_shard_api_on_torch_stream(ctx):
+    """csvb200_shard_quote_parity_device + csvb200_index_build_shard_device_ex: the carry-in parity is
+    derived on the device from the gathered parity array; everything runs on torch's current stream
+    (handle 0 = legacy default stream must NOT fall back to the context's private stream)."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    q, _ = gen.quoted(6 << 20, seed=44)
+    raw = q.tobytes()
+    want = O.closed_form_numpy(raw)
+    n = len(raw)
+    G = 5
+    cuts = [0] + [(k * n) // G + 37 * k + 13 for k in range(1, G)] + [n]
+    # make at least one cut land inside a quoted field
+    inside = raw.index(b'"', cuts[2]) + 1
+    cuts[2] = inside
+    for stream in (torch.cuda.current_stream(dev), torch.cuda.Stream(dev)):
+        with torch.cuda.stream(stream):
+            ctx.set_stream(stream.cuda_stream)
+            try:
+                shards = [torch.from_numpy(np.frombuffer(raw, dtype=np.uint8)[cuts[k]:cuts[k + 1]].copy()).to(dev)
+                          for k in range(G)]
+                pars = torch.full((G,), 7, dtype=torch.int32, device=dev)   # garbage: pass A must overwrite it
+                for k in range(G):
+                    ctx.shard_quote_parity_device(shards[k].data_ptr(), shards[k].numel(), pars[k:].data_ptr())
+                res = torch.zeros((G, 2), dtype=torch.int64, device=dev)
+                idxs = [ctx.index_build_shard_device_ex(shards[k].data_ptr(), shards[k].numel(), pars.data_ptr(), k,
+                                                        cuts[k], k == 0, res[k].data_ptr()) for k in range(G)]
+                got = np.concatenate([i.to_host() for i in idxs])
+                assert got.shape == want.shape and (got == want).all()
+                ps = pars.cpu().tolist()
+                assert ps == [O.shard_summary(raw[cuts[k]:cuts[k + 1]])[0] for k in range(G)] and 1 in ps
+                counts = res[:, 0].cpu().tolist()
+                assert counts == [len(i) - (1 if k == 0 else 0) for k, i in enumerate(idxs)]
+                assert res[-1, 1].item() == (raw.count(b'"') & 1)
+                for i in idxs:
+                    i.free()
+            finally:
+                ctx.set_stream(None)
