@@ -35,6 +35,32 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+HOST_SO = os.path.join(HERE, "libcsvsimd_host.so")
+HOST_SOURCES = [os.path.join("host", "host_capi.cpp")]
+HOST_HEADERS = [os.path.join("host", "csv_simd.hpp")]
+
+
+def host_is_stale() -> bool:
+    if not os.path.exists(HOST_SO):
+        return True
+    t = os.path.getmtime(HOST_SO)
+    deps = [os.path.join(CSRC, s) for s in HOST_SOURCES + HOST_HEADERS] + [SO]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_host(force: bool = False) -> str:
+    """The C++ host mirror of the crate's API (csrc/host/csv_simd.hpp) + its flat C shim, linked against
+    libcsvb200.so (rpath $ORIGIN)."""
+    build(force=False)
+    if not force and not host_is_stale():
+        return HOST_SO
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_SO,
+           *[os.path.join(CSRC, s) for s in HOST_SOURCES], "-L" + HERE, "-lcsvb200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return HOST_SO
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
@@ -48,4 +74,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
+    build_host(force="--force" in sys.argv)
     print(SO)
+    print(HOST_SO)
