@@ -448,10 +448,10 @@ int csvb200_index_build(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, u
     return CSVB200_OK;
 }
 
-int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap,
+// Simple (non-overlapped) form: build on the device, then copy the index out.
+static int build_to_host_serial(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap,
                                 size_t* len_out)
 {
-    if (!ctx || !len_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     csvb200_index* idx = nullptr;
     int rc = csvb200_index_build(ctx, host_bytes, n, CSVB200_BUILD_DEFAULT, &idx);
     if (rc) return rc;
@@ -460,6 +460,111 @@ int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
                              : fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
     csvb200_index_free(idx);
     return rc;
+}
+
+// End-to-end pipeline: the input goes up in kE2eChunk pieces, each piece is indexed by its own launch
+// chained to the previous one through a device-resident carry cell {entries so far, quote parity}
+// (no host round trip between launches), and every finished index segment goes down on a second
+// stream while later pieces are still going up -- PCIe is full duplex, so the step costs about
+// max(H2D, D2H) instead of their sum.
+int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap,
+                                size_t* len_out)
+{
+    if (!ctx || !len_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    const size_t nchunks = (n + kE2eChunk - 1) / kE2eChunk;
+    if (nchunks < 2 || nchunks + 1 >= kCells || !dst) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s_up = ctx->stream, s_down = ctx->copy_stream;
+    uint8_t* d_bytes = nullptr;
+    uint64_t* d_index = nullptr;
+    const size_t cap = initial_cap(ctx, n);
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, s_up));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_index, cap * sizeof(uint64_t), s_up));
+    CU_TRY(ctx, cudaMemsetAsync(d_index, 0, sizeof(uint64_t), s_up));  // sentinel (src/reader.rs:216)
+    // cells: cell0 = carry into chunk 0 = {0, 0}; cell[c+1] = result of chunk c
+    const size_t cell0 = ctx->next_cell + nchunks + 1 <= kCells ? ctx->next_cell : 0;
+    ctx->next_cell = (cell0 + nchunks + 1) % kCells;
+    uint64_t* d_cells = ctx->d_cells + cell0 * kCellWords;
+    uint64_t* h_cells = ctx->h_cells + cell0 * kCellWords;
+    CU_TRY(ctx, cudaMemsetAsync(d_cells, 0, kCellWords * sizeof(uint64_t), s_up));
+    std::vector<cudaEvent_t> done(nchunks, nullptr);
+    int rc = CSVB200_OK;
+    auto cleanup = [&]() {
+        for (cudaEvent_t e : done)
+            if (e) cudaEventDestroy(e);
+        cudaStreamSynchronize(s_down);
+        cudaFreeAsync(d_bytes, s_up);
+        cudaFreeAsync(d_index, s_up);
+    };
+    // ---- enqueue every upload + launch; nothing here waits on the host ----
+    for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
+        const size_t off = c * kE2eChunk, len = std::min(kE2eChunk, n - off);
+        rc = upload(ctx, d_bytes + off, host_bytes + off, len);
+        if (rc) break;
+        const uint64_t num_tiles = (len + kTileBytes - 1) / kTileBytes;
+        const size_t sbytes = 128 + num_tiles * kDescStride * sizeof(uint64_t);
+        rc = ensure_scratch(ctx, sbytes);
+        if (rc) break;
+        cudaError_t e = cudaMemsetAsync(ctx->d_scratch, 0, sbytes, s_up);
+        BuildParams p{};
+        p.in = d_bytes + off;
+        p.n = len;
+        p.index = d_index;
+        p.cap = cap;
+        p.out_base = 1;
+        p.pos_bias = off;
+        p.carry = d_cells + c * kCellWords;
+        p.num_tiles = (uint32_t)num_tiles;
+        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
+        p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
+        p.result = d_cells + (c + 1) * kCellWords;
+        p.tune = ctx->tune;
+        bool use_tma = tma_path_usable(len);
+        if (ctx->kernel_override == 1) use_tma = false;
+        if (e == cudaSuccess) e = use_tma ? launch_index_build_tma(p, s_up) : launch_index_build(p, s_up);
+        ctx->launches += 1;
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h_cells + (c + 1) * kCellWords, d_cells + (c + 1) * kCellWords, 2 * sizeof(uint64_t),
+                                cudaMemcpyDeviceToHost, s_up);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(done[c], s_up);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
+        }
+    }
+    // ---- as each chunk's kernel finishes, send its index segment down on the second stream ----
+    size_t copied = 0;  // entries already on their way to dst (including the sentinel)
+    bool overflow = false, dst_small = false;
+    for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
+        cudaError_t e = cudaEventSynchronize(done[c]);
+        if (e == cudaSuccess) {
+            const size_t upto = 1 + (size_t)h_cells[(c + 1) * kCellWords];  // entries through this chunk
+            if (upto > cap) overflow = true;
+            if (upto > dst_cap) dst_small = true;
+            if (!overflow && !dst_small && upto > copied) {
+                e = cudaStreamWaitEvent(s_down, done[c], 0);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(dst + copied, d_index + copied, (upto - copied) * sizeof(uint64_t),
+                                        cudaMemcpyDeviceToHost, s_down);
+                copied = upto;
+            }
+            if (c + 1 == nchunks) *len_out = upto;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
+        }
+    }
+    if (rc == CSVB200_OK) {
+        cudaError_t e = cudaStreamSynchronize(s_down);
+        if (e != cudaSuccess) rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
+    }
+    cleanup();
+    if (rc) return rc;
+    if (overflow) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);  // denser than the reserve
+    if (dst_small) return fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    return CSVB200_OK;
 }
 
 int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t* parity_out)

@@ -398,3 +398,27 @@ def test_stream_ordered_shard_api_on_torch_stream(ctx):
                     i.free()
             finally:
                 ctx.set_stream(None)
+
+
+def test_build_to_host_pipeline_multi_chunk(ctx):
+    """csvb200_index_build_to_host: chunked H2D / chained launches / overlapped D2H (3 chunks of 64 MiB),
+    quote regions and odd output bases crossing the chunk boundaries; pageable and pinned buffers."""
+    import torch
+    data, _ = gen.quoted(150 << 20, seed=43)
+    n = data.size
+    want = O.read_sse(data)
+    out = np.zeros(want.size + 16, dtype=np.uint64)
+    ln = ctx.index_build_to_host(data.ctypes.data, n, out.ctypes.data, out.size)      # pageable in / out
+    assert ln == want.size and (out[:ln] == want).all()
+    h_in = torch.from_numpy(data).pin_memory()
+    h_out = torch.zeros(want.size + 16, dtype=torch.int64).pin_memory()
+    ln = ctx.index_build_to_host(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel())  # pinned in / out
+    assert ln == want.size and (h_out.numpy()[:ln].view(np.uint64) == want).all()
+    with pytest.raises(BufferError):
+        ctx.index_build_to_host(h_in.data_ptr(), n, h_out.data_ptr(), 1000)
+    # dense input overflows the reserve heuristic: transparent fallback to the exact-size path
+    dense = np.full(130 << 20, 0x2C, dtype=np.uint8)
+    out = np.zeros(dense.size + 2, dtype=np.uint64)
+    ln = ctx.index_build_to_host(dense.ctypes.data, dense.size, out.ctypes.data, out.size)
+    assert ln == dense.size + 1 and out[1] == 0 and out[ln - 1] == dense.size - 1
+    assert (np.diff(out[1:ln].astype(np.int64)) == 1).all()
