@@ -130,6 +130,20 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload: str, n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the hot kernel, from the committed
+    ncu --set full capture of the same 1 GiB workload (profiles/); None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_v4_traffic.json")) as f:
+            t = json.load(f)
+        key = "cfg2" if workload == "cfg2_unquoted" else "cfg3"
+        if abs(n - GiB) > (1 << 20) or workload == "cfg4_sharded":
+            return None
+        return t[key]["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def host_cpu():
     model = "unknown"
     try:
@@ -341,8 +355,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "index_entries": E_total, "index_entry_bytes": 8,
                        "l2_policy": "input (1 GiB) and index (>= 0.5 GB) are far larger than the 126 MB L2; no flush",
                        "parallelism": f"byte-range shards x{world}" if world > 1 else "single GPU"},
-            "roofline": {"bound": "hbm", "kernel": "index_build_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "index_build_tma_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(wl, n), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                          "csv_gbs_kernel_only": n / (k_ms * 1e-3) / 1e9},
             "cpu_baseline": cpu,

@@ -458,6 +458,30 @@ int oracle_seek_field(const uint64_t *index, size_t index_len, size_t data_len,
     return 0;
 }
 
+/* Timed CPU baseline for the batched-lookup config: the scalar seek_field above over nq queries,
+ * single thread, no printing.  Returns a checksum (sum of start ^ end over the hits) and the hit count. */
+int oracle_seek_fields_timed(const uint64_t *index, size_t index_len, size_t data_len,
+                             uint32_t record_cnt, uint32_t field_cnt, int crlf,
+                             const uint32_t *rec, const uint32_t *fld, size_t nq,
+                             uint64_t *checksum, uint64_t *hits)
+{
+    uint64_t cs = 0, h = 0;
+    for (size_t i = 0; i < nq; ++i) {
+        uint64_t s, e;
+        int found;
+        const int rc = oracle_seek_field(index, index_len, data_len, record_cnt, field_cnt, crlf,
+                                         rec[i], fld[i], &s, &e, &found);
+        if (rc) return rc;
+        if (found) {
+            cs += s ^ (e << 1);
+            ++h;
+        }
+    }
+    *checksum = cs;
+    *hits = h;
+    return 0;
+}
+
 /* src/tape.rs:385-428 boundaries(task_size: u32, job_count: u8).
  * Returns the number of boundaries written (0 = None). out must hold 255. */
 int oracle_boundaries(uint32_t task_size, uint8_t job_count, oracle_boundary *out)

@@ -57,6 +57,10 @@ int oracle_seek_field(const uint64_t *index, size_t index_len, size_t data_len,
                       uint32_t record_cnt, uint32_t field_cnt, int crlf,
                       uint32_t record_idx, uint32_t field_idx,
                       uint64_t *start, uint64_t *end, int *found);
+int oracle_seek_fields_timed(const uint64_t *index, size_t index_len, size_t data_len,
+                             uint32_t record_cnt, uint32_t field_cnt, int crlf,
+                             const uint32_t *rec, const uint32_t *fld, size_t nq,
+                             uint64_t *checksum, uint64_t *hits);
 int oracle_boundaries(uint32_t task_size, uint8_t job_count, oracle_boundary *out);
 int oracle_chunks(uint32_t record_cnt, uint64_t jump, uint8_t num, oracle_chunk *out);
 uint64_t oracle_blsr(uint64_t x);

@@ -84,6 +84,8 @@ def lib():
                                          C.c_uint32, C.c_uint32, u64p, u64p, C.POINTER(C.c_int)]
         L.oracle_seek_field.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32,
                                         C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, C.POINTER(C.c_int)]
+        L.oracle_seek_fields_timed.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p]
         L.oracle_boundaries.argtypes = [C.c_uint32, C.c_uint8, C.POINTER(_Boundary)]
         L.oracle_chunks.argtypes = [C.c_uint32, C.c_uint64, C.c_uint8, C.POINTER(_Chunk)]
         L.oracle_blsr.argtypes = [C.c_uint64]
@@ -212,6 +214,15 @@ def seek_field(index: np.ndarray, data_len: int, record_cnt: int, field_cnt: int
     _check(lib().oracle_seek_field(index.ctypes.data, index.size, data_len, record_cnt, field_cnt, int(crlf),
                                    r & 0xFFFFFFFF, fld & 0xFFFFFFFF, C.byref(s), C.byref(e), C.byref(f)))
     return (s.value, e.value) if f.value else None
+
+
+def seek_fields_timed(index: np.ndarray, data_len: int, record_cnt: int, field_cnt: int, crlf: bool,
+                      rec: np.ndarray, fld: np.ndarray):
+    """CPU baseline of the batched lookup config: returns (checksum, hits)."""
+    cs, h = C.c_uint64(), C.c_uint64()
+    _check(lib().oracle_seek_fields_timed(index.ctypes.data, index.size, data_len, record_cnt, field_cnt, int(crlf),
+                                          rec.ctypes.data, fld.ctypes.data, rec.size, C.byref(cs), C.byref(h)))
+    return cs.value, h.value
 
 
 def boundaries(task_size: int, job_count: int):
