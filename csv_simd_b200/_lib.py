@@ -45,6 +45,10 @@ SIGNATURES = {
     "csvb200_shard_quote_parity_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "csvb200_index_build_shard_device_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32,
                                                       C.c_uint64, C.c_int, C.c_void_p, vpp]),
+    "csvb200_index_build_shard_speculative": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64,
+                                                        C.c_int, C.c_uint64, C.c_void_p, vpp]),
+    "csvb200_index_shard_verify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "csvb200_index_shard_redone": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "csvb200_index_sync": (C.c_int, [C.c_void_p]),
     "csvb200_index_len": (C.c_size_t, [C.c_void_p]),
     "csvb200_index_end_parity": (C.c_int, [C.c_void_p]),

@@ -130,6 +130,15 @@ class Context:
             int(emit_sentinel), C.c_void_p(d_result_out or 0), C.byref(h)))
         return StructureIndex(self, h)
 
+    def index_build_shard_speculative(self, dev_ptr: int, n: int, shard_rank: int, global_offset: int,
+                                      emit_sentinel: bool, d_result_out: int, predict_window: int = 0
+                                      ) -> "StructureIndex":
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_build_shard_speculative(
+            self._h, C.c_void_p(dev_ptr), n, shard_rank, global_offset, int(emit_sentinel), predict_window,
+            C.c_void_p(d_result_out), C.byref(h)))
+        return StructureIndex(self, h)
+
     # -- K1 known-answer exports ------------------------------------------------------------
     def block_masks(self, data):
         a = _as_u8(data)
@@ -195,6 +204,16 @@ class StructureIndex:
         if self._host is None:
             self._host = self.to_host()
         return self._host
+
+    def shard_verify(self, d_gathered: int, world: int, d_final_out: int = 0):
+        self.ctx._check(self._lib.csvb200_index_shard_verify(self._h, C.c_void_p(d_gathered), world,
+                                                             C.c_void_p(d_final_out or 0)))
+
+    def shard_redone(self):
+        """(misprediction rebuild ran?, true carry-in parity) of a speculative shard build."""
+        r, c = C.c_int(), C.c_int()
+        self.ctx._check(self._lib.csvb200_index_shard_redone(self._h, C.byref(r), C.byref(c)))
+        return bool(r.value), c.value
 
     def copy_out_ptr(self, dst_ptr: int, dst_cap: int):
         self.ctx._check(self._lib.csvb200_index_copy_out(self._h, C.c_void_p(dst_ptr), dst_cap))

@@ -18,8 +18,10 @@
 using namespace csvb200;
 
 namespace {
-constexpr size_t kCells = 4096;              // ring of result cells (4 x u64 each)
+constexpr size_t kCells = 4096;              // result cells (4 x u64 each): a ring of kRingCells + one scratch cell
 constexpr size_t kCellWords = 4;
+constexpr size_t kRingCells = kCells - 1;    // the last cell is the out-of-bounds flag of the async seek calls
+constexpr uint64_t kDefaultPredictWindow = 64u << 10;
 constexpr size_t kStageBytes = 32u << 20;    // pinned staging buffers for pageable input
 constexpr int kStageBufs = 2;
 constexpr size_t kE2eChunk = 64u << 20;      // H2D / kernel / D2H pipeline granularity
@@ -64,6 +66,10 @@ struct csvb200_index {
     const uint32_t* d_shard_par = nullptr;  // device-resident shard parities (multi-GPU), or null
     uint32_t shard_rank = 0;
     uint64_t* d_result2 = nullptr;          // optional caller-owned device copy of {count, parity}
+    // speculative sharded build: carry cell {0, carry parity, decisive quote found, redo flag} (device / pinned mirror)
+    bool speculative = false;
+    bool verified = false;
+    size_t carry_cell = 0;
     uint8_t* d_bytes_owned = nullptr;
     // Tape metadata (TapeCore::init)
     bool tape_ready = false;
@@ -109,13 +115,14 @@ size_t initial_cap(const csvb200_ctx* ctx, size_t n)
 }
 
 // enqueue one build of idx->src[0..n) into idx->d_index (capacity idx->cap)
-int enqueue_build(csvb200_index* idx, bool timed)
+// redo = the conditional second launch of a speculative shard build (runs only if the carry prediction was wrong)
+int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
 {
     csvb200_ctx* ctx = idx->ctx;
     const size_t n = idx->n;
     uint64_t num_tiles = (n + kTileBytes - 1) / kTileBytes;
     // an empty shard still runs one (empty) tile when its carry / result live on the device
-    if (num_tiles == 0 && (idx->d_shard_par || idx->d_result2)) num_tiles = 1;
+    if (num_tiles == 0 && (idx->d_shard_par || idx->d_result2 || idx->speculative)) num_tiles = 1;
     if (num_tiles > 0xffffffffull) return fail(ctx, CSVB200_ERR_INVALID_ARG, "input too large for one launch");
     uint64_t* d_cell = ctx->d_cells + idx->cell * kCellWords;
     uint64_t* h_cell = ctx->h_cells + idx->cell * kCellWords;
@@ -143,9 +150,22 @@ int enqueue_build(csvb200_index* idx, bool timed)
         p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
         p.result = d_cell;
         p.result2 = idx->d_result2;
+        p.result2_words = 2;
         p.shard_par = idx->d_shard_par;
         p.shard_rank = idx->shard_rank;
         p.tune = ctx->tune;
+        if (idx->speculative) {
+            uint64_t* d_carry = ctx->d_cells + idx->carry_cell * kCellWords;
+            p.carry = d_carry;
+            p.result2_words = 4;
+            if (redo) {
+                p.run_flag = reinterpret_cast<const uint32_t*>(d_carry + 3);
+            } else if (!idx->verified && idx->d_result2) {
+                // first (speculative) launch: also accumulate the shard's separator total
+                CU_TRY(ctx, cudaMemsetAsync(idx->d_result2, 0, 4 * sizeof(uint64_t), ctx->stream));
+                p.total_out = reinterpret_cast<unsigned long long*>(idx->d_result2 + 3);
+            }
+        }
         if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
         // kernel choice: the TMA pipeline for anything of size, the one-tile-per-CTA kernel for small
         // inputs; CSVB200_KERNEL=simple|tma forces one (tests cross-check the two against each other)
@@ -174,7 +194,7 @@ int new_index(csvb200_ctx* ctx, csvb200_index** out)
     if (!idx) return fail(ctx, CSVB200_ERR_OOM, "host allocation failed");
     idx->ctx = ctx;
     idx->cell = ctx->next_cell;
-    ctx->next_cell = (ctx->next_cell + 1) % kCells;
+    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
     cudaError_t e = cudaEventCreateWithFlags(&idx->done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete idx;
@@ -186,7 +206,8 @@ int new_index(csvb200_ctx* ctx, csvb200_index** out)
 
 int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity, uint64_t pos_bias,
                         int emit_sentinel, csvb200_index** out, const uint32_t* d_shard_par = nullptr,
-                        uint32_t shard_rank = 0, uint64_t* d_result2 = nullptr)
+                        uint32_t shard_rank = 0, uint64_t* d_result2 = nullptr, bool speculative = false,
+                        uint64_t predict_window = 0)
 {
     if (!ctx || !out || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     if ((reinterpret_cast<uintptr_t>(dev_bytes) & 15u) != 0)
@@ -203,6 +224,25 @@ int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint3
     idx->d_shard_par = d_shard_par;
     idx->shard_rank = shard_rank;
     idx->d_result2 = d_result2;
+    if (speculative) {
+        // predicted carry-in parity (rank 0: known to be 0) in a device cell the build launch reads
+        idx->speculative = true;
+        idx->carry_cell = ctx->next_cell;
+        ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+        uint64_t* d_carry = ctx->d_cells + idx->carry_cell * kCellWords;
+        cudaError_t e = cudaSuccess;
+        if (shard_rank == 0 || n == 0) {
+            e = cudaMemsetAsync(d_carry, 0, kCellWords * sizeof(uint64_t), ctx->stream);
+        } else {
+            e = launch_predict_carry(idx->src, n, predict_window ? predict_window : kDefaultPredictWindow, d_carry, ctx->stream);
+            ctx->launches += 1;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            csvb200_index_free(idx);
+            return fail(ctx, CSVB200_ERR_CUDA, std::string("carry prediction: ") + cudaGetErrorString(e));
+        }
+    }
     idx->cap = initial_cap(ctx, n);
     cudaError_t e = cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream);
     if (e != cudaSuccess) {
@@ -409,6 +449,45 @@ int csvb200_index_build_shard_device_ex(csvb200_ctx* ctx, const void* dev_bytes,
                                d_result_out);
 }
 
+int csvb200_index_build_shard_speculative(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t shard_rank,
+                                          uint64_t global_offset, int emit_sentinel, uint64_t predict_window,
+                                          uint64_t* d_result_out, csvb200_index** out)
+{
+    if (ctx && !d_result_out) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null result array");
+    return build_device_common(ctx, dev_bytes, n, 0u, global_offset, emit_sentinel, out, nullptr, shard_rank, d_result_out,
+                               true, predict_window);
+}
+
+int csvb200_index_shard_verify(csvb200_index* idx, const uint64_t* d_gathered, uint32_t world, uint64_t* d_final_out)
+{
+    if (!idx) return CSVB200_ERR_INVALID_ARG;
+    csvb200_ctx* ctx = idx->ctx;
+    if (!idx->speculative) return fail(ctx, CSVB200_ERR_INVALID_STATE, "index was not built speculatively");
+    if (!d_gathered || idx->shard_rank >= world) return fail(ctx, CSVB200_ERR_INVALID_ARG, "bad gathered array / world size");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    uint64_t* d_carry = ctx->d_cells + idx->carry_cell * kCellWords;
+    uint64_t* h_carry = ctx->h_cells + idx->carry_cell * kCellWords;
+    CU_TRY(ctx, launch_verify_carry(d_gathered, world, idx->shard_rank, d_carry, d_final_out, ctx->stream));
+    ctx->launches += 1;
+    idx->verified = true;
+    CU_TRY(ctx, cudaMemcpyAsync(h_carry, d_carry, kCellWords * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    // the rebuild with the true carry is enqueued unconditionally and exits at once when the flag is 0
+    return enqueue_build(idx, false, true);
+}
+
+int csvb200_index_shard_redone(csvb200_index* idx, int* redone, int* carry_parity)
+{
+    if (!idx) return CSVB200_ERR_INVALID_ARG;
+    if (!idx->speculative || !idx->verified)
+        return fail(idx->ctx, CSVB200_ERR_INVALID_STATE, "csvb200_index_shard_verify has not been called");
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    const uint64_t* h_carry = idx->ctx->h_cells + idx->carry_cell * kCellWords;
+    if (redone) *redone = (int)(h_carry[3] & 1u);
+    if (carry_parity) *carry_parity = (int)(h_carry[1] & 1u);
+    return CSVB200_OK;
+}
+
 int csvb200_shard_quote_parity_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t* d_parity_out)
 {
     if (!ctx || !d_parity_out || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
@@ -472,7 +551,7 @@ int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
 {
     if (!ctx || !len_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     const size_t nchunks = (n + kE2eChunk - 1) / kE2eChunk;
-    if (nchunks < 2 || nchunks + 1 >= kCells || !dst) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);
+    if (nchunks < 2 || nchunks + 1 >= kRingCells || !dst) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s_up = ctx->stream, s_down = ctx->copy_stream;
     uint8_t* d_bytes = nullptr;
@@ -482,8 +561,8 @@ int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
     CU_TRY(ctx, cudaMallocAsync((void**)&d_index, cap * sizeof(uint64_t), s_up));
     CU_TRY(ctx, cudaMemsetAsync(d_index, 0, sizeof(uint64_t), s_up));  // sentinel (src/reader.rs:216)
     // cells: cell0 = carry into chunk 0 = {0, 0}; cell[c+1] = result of chunk c
-    const size_t cell0 = ctx->next_cell + nchunks + 1 <= kCells ? ctx->next_cell : 0;
-    ctx->next_cell = (cell0 + nchunks + 1) % kCells;
+    const size_t cell0 = ctx->next_cell + nchunks + 1 <= kRingCells ? ctx->next_cell : 0;
+    ctx->next_cell = (cell0 + nchunks + 1) % kRingCells;
     uint64_t* d_cells = ctx->d_cells + cell0 * kCellWords;
     uint64_t* h_cells = ctx->h_cells + cell0 * kCellWords;
     CU_TRY(ctx, cudaMemsetAsync(d_cells, 0, kCellWords * sizeof(uint64_t), s_up));
@@ -574,7 +653,7 @@ int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n
         return fail(ctx, CSVB200_ERR_INVALID_ARG, "device input must be 16-byte aligned");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t cell = ctx->next_cell;
-    ctx->next_cell = (ctx->next_cell + 1) % kCells;
+    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
     uint64_t* d_cell = ctx->d_cells + cell * kCellWords;
     uint64_t* h_cell = ctx->h_cells + cell * kCellWords;
     CU_TRY(ctx, cudaMemsetAsync(d_cell, 0, sizeof(uint64_t), ctx->stream));

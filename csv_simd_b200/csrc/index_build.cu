@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
 
+    if (p.run_flag != nullptr && *p.run_flag == 0u) return;   // conditional redo that is not needed
     // dynamic tile id: a tile only ever waits on tiles whose CTAs already started
     if (tid == 0) sm.tile = atomicAdd(p.ticket, 1u);
     __syncthreads();
@@ -195,13 +196,9 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
             sm.tot0 = o0;
             sm.tot1 = o1;
             if (tile == p.num_tiles - 1) {
-                p.result[0] = cend;
-                p.result[1] = pend;
-                if (p.result2 != nullptr) {
-                    p.result2[0] = cend;
-                    p.result2[1] = pend;
-                }
+                write_result(p, cend, pend);
             }
+            if (p.total_out != nullptr && (o0 | o1) != 0u) atomicAdd(p.total_out, (unsigned long long)(o0 + o1));
         }
     }
     __syncthreads();
@@ -287,6 +284,128 @@ __global__ void __launch_bounds__(256) quote_parity_kernel(const uint8_t* __rest
     }
 }
 
+// ---- speculative carry for the sharded build -----------------------------------------------------
+// In RFC-4180-shaped data a quote whose neighbours are (delimiter, non-delimiter-non-quote) opens a
+// field and one whose neighbours are (non-delimiter-non-quote, delimiter) closes one; quotes touching
+// another quote ("" escapes, empty fields) and quotes between two delimiters are ambiguous and skipped.
+// The first decisive quote in the shard's first `window` bytes fixes the parity entering the shard.
+// This is only a PREDICTION: the build that uses it reports its end parity and the carry it used, the
+// true carry chain is verified after the all-gather (verify_carry_kernel) and a wrong guess is rebuilt,
+// so the result is exact for any input (the reference's toggle semantics, src/avx/stage1.rs:363-407,
+// do not require well-formed CSV).
+//
+// One CTA of 1024 threads, 16 bytes per thread and round (16 KiB per round, coalesced 128-bit loads).
+// cell = {0 (entry count entering the shard), predicted parity, 1 if a decisive quote was found, 0}.
+constexpr int kPredictThreads = 1024;
+
+__global__ void __launch_bounds__(kPredictThreads) predict_carry_kernel(const uint8_t* __restrict__ in, uint64_t n,
+                                                                        uint64_t window, uint64_t* __restrict__ cell)
+{
+    __shared__ uint32_t s_warp[kPredictThreads / 32];
+    __shared__ uint32_t s_res[3];   // found, predicted parity, running parity
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t lim = n < window ? n : window;
+    uint32_t run_par = 0u, pred = 0u, found = 0u;
+    for (uint64_t base = 0; base < lim; base += 16ull * kPredictThreads) {
+        const uint64_t i0 = base + 16ull * tid;
+        uint32_t qm = 0u, am = 0u, bm = 0u;
+        if (i0 < lim) {
+            uint8_t b[18];
+            b[0] = i0 > 0 ? in[i0 - 1] : 0x22u;   // shard edges: treated as ambiguous
+            if (i0 + 16 <= n) {
+                const uint4 v = ldg_stream_128(in + i0);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) b[1 + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) b[1 + k] = i0 + k < n ? in[i0 + k] : 0x22u;
+            }
+            b[17] = i0 + 16 < n ? in[i0 + 16] : 0x22u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t c = b[1 + k], prv = b[k], nxt = b[2 + k];
+                const bool isq = c == 0x22u && i0 + k < lim;
+                const bool dp = prv == 0x2Cu || prv == 0x0Du || prv == 0x0Au;
+                const bool dn = nxt == 0x2Cu || nxt == 0x0Du || nxt == 0x0Au;
+                const bool clean = isq && prv != 0x22u && nxt != 0x22u;
+                qm |= (isq ? 1u : 0u) << k;
+                am |= (clean && dp && !dn ? 1u : 0u) << k;   // opening
+                bm |= (clean && !dp && dn ? 1u : 0u) << k;   // closing
+            }
+        }
+        // thread: first decisive quote, quote parity before it, quote parity of the whole chunk
+        const uint32_t dec = am | bm;
+        const uint32_t f = dec ? (uint32_t)__ffs((int)dec) - 1u : 0u;
+        const uint32_t t_before = __popc(qm & ((1u << f) - 1u)) & 1u;
+        const uint32_t t_open = (am >> f) & 1u;
+        const uint32_t t_par = __popc(qm) & 1u;
+        // warp: nearest decisive lane
+        const uint32_t bal = __ballot_sync(0xffffffffu, dec != 0u);
+        const uint32_t pb = __ballot_sync(0xffffffffu, t_par != 0u);
+        const uint32_t fl = bal ? (uint32_t)__ffs((int)bal) - 1u : 0u;
+        const uint32_t w_before = (__popc(pb & ((1u << fl) - 1u)) & 1u) ^ __shfl_sync(0xffffffffu, t_before, (int)fl);
+        const uint32_t w_open = __shfl_sync(0xffffffffu, t_open, (int)fl);
+        if (lane == 0) s_warp[warp] = (bal ? 1u : 0u) | (w_open << 1) | (w_before << 2) | ((__popc(pb) & 1u) << 3);
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = run_par, fnd = 0u, prd = 0u;
+            for (int w = 0; w < kPredictThreads / 32; ++w) {
+                const uint32_t v = s_warp[w];
+                if (v & 1u) {
+                    const uint32_t before = acc ^ ((v >> 2) & 1u);   // quotes in shard[0 .. i) mod 2
+                    prd = ((v >> 1) & 1u) ? before : (before ^ 1u);
+                    fnd = 1u;
+                    break;
+                }
+                acc ^= (v >> 3) & 1u;
+            }
+            s_res[0] = fnd;
+            s_res[1] = prd;
+            s_res[2] = acc;
+        }
+        __syncthreads();
+        found = s_res[0];
+        pred = s_res[1];
+        run_par = s_res[2];
+        if (found) break;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        cell[0] = 0ull;
+        cell[1] = pred;
+        cell[2] = found;
+        cell[3] = 0ull;
+    }
+}
+
+// After the all-gather of every rank's {entries emitted under the carry it used, end parity under that
+// carry, carry used, total separators}: derive the TRUE carry of every shard (exclusive XOR-scan of
+// the shard parities, shard parity = end ^ used) and, because flipping a shard's carry turns "outside"
+// separators into "inside" ones and vice versa (c0 + c1 = total), the true entry count of every shard
+// without another exchange.  cell <- {0, true carry of this rank, -, redo flag}; final[world][2]
+// (optional) <- {true entry count, true carry} of every rank.
+__global__ void verify_carry_kernel(const uint64_t* __restrict__ gathered, uint32_t world, uint32_t rank,
+                                    uint64_t* __restrict__ cell, uint64_t* __restrict__ final_out)
+{
+    if (threadIdx.x != 0) return;
+    uint32_t carry = 0u;
+    for (uint32_t j = 0; j < world; ++j) {
+        const uint64_t cnt = gathered[4 * j + 0], total = gathered[4 * j + 3];
+        const uint32_t endp = (uint32_t)(gathered[4 * j + 1] & 1ull), used = (uint32_t)(gathered[4 * j + 2] & 1ull);
+        if (final_out != nullptr) {
+            final_out[2 * j + 0] = carry == used ? cnt : total - cnt;
+            final_out[2 * j + 1] = carry;
+        }
+        if (j == rank) {
+            cell[0] = 0ull;
+            cell[1] = carry;
+            cell[3] = carry != used ? 1ull : 0ull;
+        }
+        carry ^= endp ^ used;
+    }
+}
+
 // ---- K1 known-answer exports --------------------------------------------------
 // quote_bits / all_struct words per 64-byte block, as get_struct_positions(16|3)
 // returns them (avx/stage1.rs:392,394); bytes past n read as zero.
@@ -345,6 +464,19 @@ cudaError_t launch_quote_parity(const uint8_t* in, uint64_t n, uint32_t* out, cu
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks == 0) blocks = 1;
     quote_parity_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_predict_carry(const uint8_t* in, uint64_t n, uint64_t window, uint64_t* cell, cudaStream_t stream)
+{
+    predict_carry_kernel<<<1, kPredictThreads, 0, stream>>>(in, n, window, cell);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_verify_carry(const uint64_t* gathered, uint32_t world, uint32_t rank, uint64_t* cell,
+                                uint64_t* final_out, cudaStream_t stream)
+{
+    verify_carry_kernel<<<1, 32, 0, stream>>>(gathered, world, rank, cell, final_out);
     return cudaGetLastError();
 }
 

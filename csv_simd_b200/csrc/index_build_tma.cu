@@ -209,6 +209,8 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
 
+    if (p.run_flag != nullptr && *p.run_flag == 0u) return;   // conditional redo that is not needed
+
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < kStages; ++i) {
@@ -250,6 +252,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
         }
     } else if (warp == kLookbackWarp) {
         // ===== scan of warp aggregates + decoupled look-back =====
+        uint64_t cta_total = 0ull;   // separators (inside + outside quotes) of this CTA's super-tiles (lane 0)
         for (uint32_t it = 0;; ++it) {
             const uint32_t b = it % kRing;
             mbar_wait(&sm.agg_full[b], (it / kRing) & 1u);
@@ -303,18 +306,13 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                     pi.base[sub] = b0;
                     pi.cnt[sub] = (uint32_t)(b1 - b0);
                 }
-                if (tile == p.num_tiles - 1) {
-                    p.result[0] = cend;
-                    p.result[1] = pend;
-                    if (p.result2 != nullptr) {
-                        p.result2[0] = cend;
-                        p.result2[1] = pend;
-                    }
-                }
+                if (tile == p.num_tiles - 1) write_result(p, cend, pend);
+                cta_total += (uint64_t)(o0 + o1);
                 mbar_arrive(&sm.pref_full[b]);
             }
             __syncwarp();
         }
+        if (lane == 0 && p.total_out != nullptr && cta_total != 0ull) atomicAdd(p.total_out, (unsigned long long)cta_total);
     } else {
         // ===== workers =====
         const uint64_t full_rows = p.n >> 7;

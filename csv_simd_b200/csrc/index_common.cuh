@@ -54,6 +54,19 @@ __device__ __forceinline__ uint64_t virtual_prefix_desc(const BuildParams& p)
     return kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
 }
 
+// Called by the thread that resolved the LAST tile of a launch: entries emitted through the end of the
+// launch, the quote parity after its last byte and (4-word form) the carry parity the launch used.
+__device__ __forceinline__ void write_result(const BuildParams& p, uint64_t cend, uint32_t pend)
+{
+    p.result[0] = cend;
+    p.result[1] = pend;
+    if (p.result2 != nullptr) {
+        p.result2[0] = cend;
+        p.result2[1] = pend;
+        if (p.result2_words >= 3u) p.result2[2] = (virtual_prefix_desc(p) >> 61) & 1ull;
+    }
+}
+
 // Warp-parallel decoupled look-back over the monoid (p, c0, c1) (see index_build.cu header).
 // Called by one full warp after the tile's own aggregate has been published; returns the quote
 // parity entering the tile (pin) and the number of index entries emitted before it (base).

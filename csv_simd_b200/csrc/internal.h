@@ -43,11 +43,18 @@ struct BuildParams {
     uint32_t* ticket;        // dynamic tile counter, zeroed before launch
     uint64_t* result;        // {entries emitted through the end of this launch, end parity}
     uint64_t* result2;       // optional second copy of `result` in caller-owned device memory
+    uint32_t result2_words;  // 2, or 4: {entries, end parity, carry parity used, (total separators via total_out)}
+    // optional: every CTA adds the separator count (inside + outside quotes) of its tiles; zeroed by the
+    // caller.  With it the entry count under the OTHER carry parity is total - entries (c0 + c1 = total).
+    unsigned long long* total_out;
     // multi-GPU: quote parities of all shards as all-gathered on the device; the carry-in parity of
     // this shard is the XOR of shard_par[0 .. shard_rank) (overrides carry_parity when non-null)
     const uint32_t* shard_par;
     uint32_t shard_rank;
     uint32_t tune;           // experiment knob (CSVB200_TUNE)
+    // speculative multi-GPU build: when non-null the launch is a conditional redo and exits at once
+    // unless *run_flag != 0 (the carry prediction turned out wrong)
+    const uint32_t* run_flag;
 };
 
 // one tile per CTA, plain loads: small inputs and cross-check of the TMA kernel
@@ -58,6 +65,15 @@ bool tma_path_usable(uint64_t n);
 
 // quote parity of a byte range (pass A of the multi-GPU protocol); *out ^= parity
 cudaError_t launch_quote_parity(const uint8_t* in, uint64_t n, uint32_t* out, cudaStream_t stream);
+
+// speculative carry (multi-GPU): predict the quote parity entering a shard from the first unambiguous
+// quote in its first `window` bytes; cell = {0, predicted parity, 1 if a decisive quote was found}
+cudaError_t launch_predict_carry(const uint8_t* in, uint64_t n, uint64_t window, uint64_t* cell, cudaStream_t stream);
+// gathered[world][4] = {entries, end parity, carry parity used, total separators} per rank; writes
+// cell = {0, true carry of `rank`, -, redo flag (true carry != the one used)} and, when non-null,
+// final_out[world][2] = {true entry count, true carry} of every rank
+cudaError_t launch_verify_carry(const uint64_t* gathered, uint32_t world, uint32_t rank, uint64_t* cell,
+                                uint64_t* final_out, cudaStream_t stream);
 
 // debug / known-answer exports (K1): per 64-byte block quote and separator words, class bytes
 cudaError_t launch_block_masks(const uint8_t* in, uint64_t n, uint64_t* quote_words, uint64_t* sep_words,

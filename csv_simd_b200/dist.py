@@ -3,6 +3,7 @@
 Implements the reference README's undone idea "splitting work without first knowing record breaks
 (requires toggling interpretation if/when start in quoted text)" (README.md:24):
 
+two-pass protocol:
   pass A   every rank: quote parity p_k of its own shard          (csvb200_shard_quote_parity)
   exchange ONE tiny all_gather of the p_k (NCCL over NVLink; gloo in the CPU tests)
            carry-in parity of rank k = XOR of p_j for j < k
@@ -10,6 +11,13 @@ Implements the reference README's undone idea "splitting work without first know
            (csvb200_index_build_shard_device); the sentinel entry is emitted by rank 0 only
   exchange a second tiny all_gather of the per-rank entry counts -> global index base of each
            segment (needed for record numbering / lookup routing, not for pass B)
+
+speculative protocol (default; one pass over the bytes and one exchange in the common case):
+  predict  every rank guesses its carry-in parity from the first unambiguous quote of its shard
+  build    fused index build with the guess; reports {entries, end parity, carry used, separator total}
+  exchange ONE all_gather of those 32 bytes per rank
+  verify   every rank: true carries = exclusive XOR-scan of (end ^ used); true counts from
+           c0 + c1 = total; a shard whose guess was wrong (and only that shard) is re-indexed
 
 The index stays distributed: rank k holds entries [base_k, base_k + len_k) of the global index.
 No bulk data ever crosses GPUs.
@@ -62,6 +70,21 @@ def exchange_counts(local_count: int, group=None, device: Optional[torch.device]
     return exclusive_bases(cs)[dist.get_rank(group)], sum(cs)
 
 
+def verify_speculation(gathered: Sequence[Sequence[int]]):
+    """Host statement of what csvb200_index_shard_verify computes on the device (verify_carry_kernel):
+    gathered[k] = (entries emitted under the carry rank k used, end parity under that carry, carry used,
+    separator total of shard k).  Returns (true carries, true entry counts, redo flags).  A shard's
+    own quote parity is end ^ used whatever carry it guessed, and flipping its carry swaps the separators
+    inside and outside quotes, so its true count is `entries` or `total - entries`."""
+    carries, counts, redo, carry = [], [], [], 0
+    for cnt, endp, used, total in gathered:
+        carries.append(carry)
+        counts.append(int(cnt) if carry == (int(used) & 1) else int(total) - int(cnt))
+        redo.append(carry != (int(used) & 1))
+        carry ^= (int(endp) ^ int(used)) & 1
+    return carries, counts, redo
+
+
 @dataclass
 class ShardedIndex:
     local: api.StructureIndex   # this rank's segment (global byte positions)
@@ -72,19 +95,45 @@ class ShardedIndex:
 
 
 def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: int, group=None,
-                        resolve: bool = True) -> ShardedIndex:
+                        resolve: bool = True, speculative: bool = True, predict_window: int = 0) -> ShardedIndex:
     """Index this rank's shard [global_offset, global_offset + n) of a file split across the ranks
-    of `group` at arbitrary byte offsets.
+    of `group` at arbitrary byte offsets.  Everything is stream-ordered on the current CUDA stream
+    (which the Context must be bound to, see Context.set_stream); the host only synchronises once, at
+    the end, to learn the segment length (resolve=False skips even that; fields base/total_len/carry_in
+    are then -1 and `counts` holds the device tensor of per-rank {entries, carry}).
 
-    Everything between pass A and the end of pass B is stream-ordered on the current CUDA stream
-    (which the Context must be bound to, see Context.set_stream): parity kernel -> NCCL all_gather
-    of 4 bytes per rank -> build kernel that XORs the gathered parities of the lower ranks on the
-    device -> NCCL all_gather of the entry counts.  The host only synchronises once, at the end,
-    to learn the segment length (resolve=False skips even that; fields base/total_len/carry_in are
-    then -1 and `counts` holds the device tensor)."""
+    speculative=True (default): ONE exchange.  Every rank predicts its carry-in parity from the first
+    unambiguous quote of its shard, indexes at once, then a single NCCL all_gather of 32 bytes per rank
+    ({entries, end parity, carry used, separator total}) lets every rank verify the carry chain on the
+    device, derive every shard's true entry count (c0 + c1 = total) and re-index only a mispredicted
+    shard (csvb200_index_build_shard_speculative / csvb200_index_shard_verify).
+
+    speculative=False: the two-pass protocol of SURVEY.md 8e -- parity kernel -> all_gather of 4 bytes
+    per rank -> build kernel that XORs the gathered parities of the lower ranks on the device ->
+    all_gather of the entry counts."""
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     device = torch.device("cuda", ctx.device)
+    if speculative:
+        res_local = torch.empty(4, dtype=torch.int64, device=device)
+        idx = ctx.index_build_shard_speculative(dev_ptr, n, rank, global_offset, emit_sentinel=(rank == 0),
+                                                d_result_out=res_local.data_ptr(), predict_window=predict_window)
+        res_all = torch.empty(4 * world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(res_all, res_local, group=group)            # the only exchange: 32 B per rank
+        final = torch.empty(2 * world, dtype=torch.int64, device=device)
+        idx.shard_verify(res_all.data_ptr(), world, final.data_ptr())           # + conditional re-index
+        idx._keepalive = (res_local, res_all, final)
+        if not resolve:
+            out = ShardedIndex(idx, -1, -1, -1, [])
+            out.counts = final
+            return out
+        host = torch.cat([final, res_all]).cpu().tolist()                       # the only host sync
+        counts = [int(c) for c in host[0:2 * world:2]]
+        counts[0] += 1                                                          # sentinel lives on rank 0
+        carries = [int(c) for c in host[1:2 * world:2]]
+        g = host[2 * world:]
+        ps = [(int(g[4 * k + 1]) ^ int(g[4 * k + 2])) & 1 for k in range(world)]  # shard parity = end ^ carry used
+        return ShardedIndex(idx, exclusive_bases(counts)[rank], sum(counts), carries[rank], ps)
     par_local = torch.empty(1, dtype=torch.int32, device=device)
     ctx.shard_quote_parity_device(dev_ptr, n, par_local.data_ptr())              # pass A
     pars = torch.empty(world, dtype=torch.int32, device=device)

@@ -122,6 +122,25 @@ int csvb200_index_build_shard_device_ex(csvb200_ctx* ctx, const void* dev_bytes,
                                         const uint32_t* d_shard_parities, uint32_t shard_rank, uint64_t global_offset,
                                         int emit_sentinel, uint64_t* d_result_out, csvb200_index** out);
 
+/* Speculative form: no pass A in the common case, ONE all-gather per build.  The carry-in parity of
+ * the shard is PREDICTED from the first unambiguous quote in its first predict_window bytes (0 = 64 KiB;
+ * rank 0 is known to start outside quotes), the shard is indexed at once with that guess, and
+ * d_result_out (4 x u64 device words) receives {entries emitted excluding the sentinel, end parity,
+ * carry parity used, total separator count of the shard}.  After the caller has all-gathered those
+ * 32 bytes per rank into d_gathered[world][4] (NCCL, same stream order), csvb200_index_shard_verify
+ * derives the true carry of every shard on the device and re-indexes this shard only if its guess was
+ * wrong (the conditional launch exits immediately otherwise), so the result is exact for ANY input.
+ * Because flipping a shard's carry swaps its inside / outside separators, every rank also derives every
+ * shard's true entry count without a second exchange: d_final_out (optional, world x 2 u64 device
+ * words) receives {entry count excluding the sentinel, carry-in parity} per rank.  Nothing here
+ * synchronises with the host. */
+int csvb200_index_build_shard_speculative(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t shard_rank,
+                                          uint64_t global_offset, int emit_sentinel, uint64_t predict_window,
+                                          uint64_t* d_result_out, csvb200_index** out);
+int csvb200_index_shard_verify(csvb200_index* idx, const uint64_t* d_gathered, uint32_t world, uint64_t* d_final_out);
+/* diagnostics (synchronises): whether the misprediction rebuild ran, and the true carry-in parity */
+int csvb200_index_shard_redone(csvb200_index* idx, int* redone, int* carry_parity);
+
 /* ---- index object: StructureIndex (src/stage1.rs:61) --------------------------------------- */
 int csvb200_index_sync(csvb200_index* idx);
 size_t csvb200_index_len(csvb200_index* idx);          /* entries incl. the sentinel if emitted */

@@ -400,6 +400,63 @@ def test_stream_ordered_shard_api_on_torch_stream(ctx):
                 ctx.set_stream(None)
 
 
+def _speculative_chain(c, raw, cuts, dev, window=0):
+    """All shards of `raw` built speculatively on one GPU; res (G x 4) plays the all-gathered array."""
+    import torch
+    G = len(cuts) - 1
+    shards = [torch.from_numpy(np.frombuffer(raw, dtype=np.uint8)[cuts[k]:cuts[k + 1]].copy()).to(dev) for k in range(G)]
+    res = torch.full((G, 4), 99, dtype=torch.int64, device=dev)   # garbage: the build must overwrite it
+    idxs = [c.index_build_shard_speculative(shards[k].data_ptr(), shards[k].numel(), k, cuts[k], k == 0,
+                                            res[k].data_ptr(), window) for k in range(G)]
+    final = torch.zeros((G, 2), dtype=torch.int64, device=dev)
+    for i in idxs:
+        i.shard_verify(res.data_ptr(), G, final.data_ptr())
+    got = np.concatenate([i.to_host() for i in idxs])
+    redone = [i.shard_redone() for i in idxs]
+    fin = final.cpu().tolist()
+    lens = [len(i) for i in idxs]
+    for i in idxs:
+        i.free()
+    return got, redone, fin, lens
+
+
+def test_speculative_shard_build(forced_ctxs):
+    """csvb200_index_build_shard_speculative + csvb200_index_shard_verify: exact for any input; no rebuild
+    on RFC-4180-shaped data even when a cut lands inside a quoted field; a misleading quote triggers the
+    rebuild of that shard only; true counts of ALL shards are derived without a second exchange."""
+    import torch
+    for kname in ("tma", "simple"):
+        c = forced_ctxs[kname]
+        dev = torch.device("cuda", c.device)
+        q, _ = gen.quoted(6 << 20, seed=44)
+        raw = q.tobytes()
+        want = O.closed_form_numpy(raw)
+        n = len(raw)
+        G = 5
+        cuts = [0] + [(k * n) // G + 37 * k + 13 for k in range(1, G)] + [n]
+        cuts[2] = raw.index(b'"', cuts[2]) + 1            # inside (or at the edge of) a quoted field
+        got, redone, fin, lens = _speculative_chain(c, raw, cuts, dev)
+        assert got.shape == want.shape and (got == want).all()
+        true_carry = [O.shard_summary(raw[:cuts[k]])[0] for k in range(G)]
+        assert [r[1] for r in redone] == true_carry and 1 in true_carry
+        assert not any(r[0] for r in redone), "well-formed CSV must not need a rebuild"
+        assert [f[1] for f in fin] == true_carry
+        assert [f[0] + (k == 0) for k, f in enumerate(fin)] == lens
+        # misleading data: an unescaped quote after a letter and before a newline looks like a closing quote
+        raw2 = (b'aa,bb"\n,cc,dd\n' * 40000) + b'x,y\n'
+        want2 = O.closed_form_numpy(raw2)
+        cuts2 = [0, 14 * 10000 + 3, 14 * 20001 + 5, 14 * 30001 + 3, len(raw2)]   # 14-byte rows, one quote each
+        got, redone, fin, lens = _speculative_chain(c, raw2, cuts2, dev)
+        assert got.shape == want2.shape and (got == want2).all()
+        assert any(r[0] for r in redone) and not redone[0][0]
+        assert [r[1] for r in redone] == [O.shard_summary(raw2[:k])[0] for k in cuts2[:-1]]
+        assert [f[0] + (k == 0) for k, f in enumerate(fin)] == lens
+        # no quote at all inside the window / empty shard / tiny shards
+        raw3 = b"1,2,3\n" * 30000
+        got, redone, fin, lens = _speculative_chain(c, raw3, [0, 7, 7, 100, 100000, len(raw3)], dev, window=4096)
+        assert (got == O.closed_form_numpy(raw3)).all() and not any(r[0] for r in redone)
+
+
 def test_build_to_host_pipeline_multi_chunk(ctx):
     """csvb200_index_build_to_host: chunked H2D / chained launches / overlapped D2H (3 chunks of 64 MiB),
     quote regions and odd output bases crossing the chunk boundaries; pageable and pinned buffers."""

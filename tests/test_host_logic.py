@@ -89,6 +89,28 @@ def test_carry_and_base_scans_match_oracle():
         assert (seg == full[bases[k]:bases[k] + counts[k]]).all()
 
 
+def test_speculative_verify_math_matches_oracle():
+    """Any guessed carries: verify_speculation recovers the true carries and entry counts (c0 + c1 = total)."""
+    data = np.frombuffer(cases.rand_bytes(40000, 5), dtype=np.uint8)
+    cuts = [0, 7001, 7002, 19999, 33333, 40000]
+    full = O.closed_form_numpy(data)
+    for guess_bits in range(32):
+        gathered = []
+        for k in range(5):
+            shard = data[cuts[k]:cuts[k + 1]]
+            p, c0, s = O.shard_summary(shard)
+            used = 0 if k == 0 else (guess_bits >> k) & 1
+            gathered.append(((s - c0) if used else c0, p ^ used, used, s))
+        carries, counts, redo = csd.verify_speculation(gathered)
+        assert carries == csd.carry_in_parities([O.shard_summary(data[cuts[k]:cuts[k + 1]])[0] for k in range(5)])
+        assert redo == [carries[k] != gathered[k][2] for k in range(5)]
+        assert 1 + sum(counts) == full.size
+        bases = csd.exclusive_bases([counts[0] + 1] + counts[1:])
+        for k in range(5):
+            seg = O.closed_form_numpy(data[cuts[k]:cuts[k + 1]], carries[k], cuts[k], with_sentinel=(k == 0))
+            assert (seg == full[bases[k]:bases[k] + seg.size]).all()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -113,6 +135,15 @@ def _gloo_worker(rank, world, port, q):
         base, total = csd.exchange_counts(seg.size)
         full = O.closed_form_numpy(data)
         ok = total == full.size and (seg == full[base:base + seg.size]).all() and len(ps) == world
+        # speculative protocol: both ranks guess 0, ONE all_gather of 4 words, verify on every rank
+        import torch
+        mine = torch.tensor([c0, p, 0, s], dtype=torch.int64)
+        allr = torch.empty(4 * world, dtype=torch.int64)
+        dist.all_gather_into_tensor(allr, mine)
+        carries, counts, redo = csd.verify_speculation(allr.view(world, 4).tolist())
+        seg2 = O.closed_form_numpy(shard, carries[rank], lo, with_sentinel=(rank == 0))
+        ok = ok and carries[rank] == carry and counts[rank] + (rank == 0) == seg2.size and (seg2 == seg).all()
+        ok = ok and redo[rank] == (carry != 0) and 1 + sum(counts) == full.size
         q.put((rank, bool(ok), carry))
     finally:
         dist.destroy_process_group()
