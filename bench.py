@@ -210,6 +210,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from csv_simd_b200 import numa
+    numa_node = numa.bind_to_device(local_rank)   # pinned staging buffers on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = args.workload or ("cfg2_unquoted" if world == 1 else "cfg4_sharded")
@@ -354,7 +356,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "config": {"workload": wl, "description": desc, "bytes_per_gpu": n, "total_bytes": total_bytes,
                        "index_entries": E_total, "index_entry_bytes": 8,
                        "l2_policy": "input (1 GiB) and index (>= 0.5 GB) are far larger than the 126 MB L2; no flush",
-                       "parallelism": f"byte-range shards x{world}" if world > 1 else "single GPU"},
+                       "parallelism": f"byte-range shards x{world}" if world > 1 else "single GPU",
+                       "host_numa_node_rank0": numa_node},
             "roofline": {"bound": "hbm", "kernel": "index_build_tma_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(wl, n), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,

@@ -23,6 +23,17 @@ class Range(C.Structure):
     _fields_ = [("start", C.c_uint64), ("end", C.c_uint64)]
 
 
+class TapeReport(C.Structure):
+    _fields_ = [("index_len", C.c_uint64), ("jump", C.c_uint64), ("problem", C.c_uint64),
+                ("first_bad_slot", C.c_uint64), ("first_bad_record", C.c_uint64), ("first_bad_pos", C.c_uint64),
+                ("record_cnt", C.c_uint32), ("ok", C.c_uint32)]
+
+
+class Chunk(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("end", C.c_uint64), ("byte_start", C.c_uint64), ("byte_end", C.c_uint64),
+                ("record_cnt", C.c_uint32), ("id", C.c_uint8)]
+
+
 # name -> (restype, argtypes); kept in sync with include/csvb200.h (tests/test_abi.py checks it)
 SIGNATURES = {
     "csvb200_version": (C.c_int, []),
@@ -56,6 +67,8 @@ SIGNATURES = {
     "csvb200_index_copy_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "csvb200_index_free": (None, [C.c_void_p]),
     "csvb200_tape_init": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, u32p, u64p]),
+    "csvb200_tape_validate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(TapeReport)]),
+    "csvb200_tape_chunks": (C.c_int, [C.c_void_p, C.c_uint8, C.POINTER(Chunk), C.c_size_t, szp]),
     "csvb200_seek_record": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Range), C.POINTER(C.c_int)]),
     "csvb200_seek_field": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Range), C.POINTER(C.c_int)]),
     "csvb200_seek_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -64,6 +77,10 @@ SIGNATURES = {
     "csvb200_seek_records_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "csvb200_gather_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                         C.c_size_t]),
+    "csvb200_materialize_column": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                             C.c_void_p, C.c_size_t, szp]),
+    "csvb200_materialize_column_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                    C.c_void_p, C.c_void_p, C.c_size_t]),
     "csvb200_block_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "csvb200_class_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

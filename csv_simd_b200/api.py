@@ -14,6 +14,9 @@ from .errors import raise_for
 BUILD_DEFAULT = 0
 BUILD_KEEP_BYTES = 1
 BUILD_STRICT_MIN64 = 2
+FIELD_RAW = 0
+FIELD_UNQUOTE = 1
+FIELD_TRIM = 2
 
 NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
 
@@ -225,6 +228,19 @@ class StructureIndex:
         self.ctx._check(rc)
         return rc_.value, j.value
 
+    def tape_validate(self, field_cnt: int, crlf: bool) -> dict:
+        """csvb200_tape_validate: first slot whose separator class does not fit its place in the row."""
+        rep = _lib.TapeReport()
+        self.ctx._check(self._lib.csvb200_tape_validate(self._h, field_cnt, int(crlf), C.byref(rep)))
+        return {k: int(getattr(rep, k)) for k, _ in _lib.TapeReport._fields_}
+
+    def tape_chunks(self, num: int):
+        """csvb200_tape_chunks: Tape::chunks(num) (src/tape.rs:95-140) + the byte range of every chunk."""
+        arr = (_lib.Chunk * 256)()
+        n = C.c_size_t()
+        self.ctx._check(self._lib.csvb200_tape_chunks(self._h, num & 0xFF, arr, 256, C.byref(n)))
+        return [{k: int(getattr(arr[i], k)) for k, _ in _lib.Chunk._fields_} for i in range(n.value)]
+
     def seek_record(self, r: int):
         rg, f = _lib.Range(), C.c_int()
         self.ctx._check(self._lib.csvb200_seek_record(self._h, r & 0xFFFFFFFF, C.byref(rg), C.byref(f)))
@@ -257,6 +273,28 @@ class StructureIndex:
 
     def seek_records_device(self, d_rec: int, nq: int, d_out: int):
         self.ctx._check(self._lib.csvb200_seek_records_device(self._h, C.c_void_p(d_rec), nq, C.c_void_p(d_out)))
+
+    def materialize_column(self, field_idx: int, first_record: int, nrec: int, flags: int = FIELD_RAW):
+        """csvb200_materialize_column: (offsets[nrec + 1], packed values) of one column."""
+        offs = np.zeros(nrec + 1, dtype=np.uint64)
+        ln = C.c_size_t()
+        # first call sizes the output (CSVB200_ERR_CAPACITY is expected), second call fills it
+        rc = self._lib.csvb200_materialize_column(self._h, field_idx, first_record, nrec, flags, offs.ctypes.data,
+                                                  None, 0, C.byref(ln))
+        if rc not in (0, 9):
+            self.ctx._check(rc)
+        out = np.empty(ln.value, dtype=np.uint8)
+        if out.size:
+            self.ctx._check(self._lib.csvb200_materialize_column(self._h, field_idx, first_record, nrec, flags,
+                                                                 offs.ctypes.data, out.ctypes.data, out.size,
+                                                                 C.byref(ln)))
+        return offs, out
+
+    def materialize_column_device(self, field_idx: int, first_record: int, nrec: int, flags: int, d_offsets: int,
+                                  d_out: int, out_cap: int):
+        self.ctx._check(self._lib.csvb200_materialize_column_device(self._h, field_idx, first_record, nrec, flags,
+                                                                    C.c_void_p(d_offsets), C.c_void_p(d_out or 0),
+                                                                    out_cap))
 
     def gather_fields(self, rec: np.ndarray, fld: np.ndarray):
         rec = np.ascontiguousarray(rec, dtype=np.uint32)

@@ -756,6 +756,104 @@ int csvb200_tape_init(csvb200_index* idx, uint32_t field_cnt, int crlf, uint32_t
     return CSVB200_OK;
 }
 
+int csvb200_tape_validate(csvb200_index* idx, uint32_t field_cnt, int crlf, csvb200_tape_report* out)
+{
+    if (!idx || !out) return CSVB200_ERR_INVALID_ARG;
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    const uint64_t j = crlf ? (uint64_t)field_cnt + 1 : (uint64_t)field_cnt;  // src/tape.rs:318-321
+    if (j == 0 || idx->len == 0) return fail(ctx, CSVB200_ERR_INVALID_ARG, "field_cnt must be >= 1");
+    const uint8_t* bytes = idx->d_bytes_owned ? idx->d_bytes_owned : idx->src;
+    if (!bytes && idx->n) return fail(ctx, CSVB200_ERR_INVALID_STATE, "index was built without CSVB200_BUILD_KEEP_BYTES");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t cell = ctx->next_cell;
+    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+    uint64_t* d_cell = ctx->d_cells + cell * kCellWords;
+    uint64_t* h_cell = ctx->h_cells + cell * kCellWords;
+    CU_TRY(ctx, cudaMemsetAsync(d_cell, 0xff, sizeof(uint64_t), ctx->stream));
+    TapeValidateParams p{};
+    p.index = idx->d_index;
+    p.index_len = idx->len;
+    p.bytes = bytes;
+    p.n = idx->n;
+    p.pos_bias = idx->pos_bias;
+    p.jump = j;
+    p.crlf = crlf ? 1 : 0;
+    p.first_bad_slot = d_cell;
+    CU_TRY(ctx, launch_tape_validate(p, ctx->stream));
+    if (idx->len > 1) ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memset(out, 0, sizeof(*out));
+    out->index_len = idx->len;
+    out->jump = j;
+    out->record_cnt = (uint32_t)((idx->len - 1) / j);   // src/tape.rs:323-325
+    out->problem = (idx->len - 1) % j;                  // src/tape.rs:327
+    out->first_bad_slot = h_cell[0];
+    out->first_bad_record = UINT64_MAX;
+    out->first_bad_pos = UINT64_MAX;
+    if (out->first_bad_slot != UINT64_MAX) {
+        out->first_bad_record = (out->first_bad_slot - 1) / j;
+        CU_TRY(ctx, cudaMemcpyAsync(&out->first_bad_pos, idx->d_index + out->first_bad_slot, sizeof(uint64_t),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    } else if (out->problem != 0) {
+        out->first_bad_record = (idx->len - 1) / j;      // the file ends inside this record
+    }
+    out->ok = out->first_bad_slot == UINT64_MAX && out->problem == 0;
+    return CSVB200_OK;
+}
+
+int csvb200_tape_chunks(csvb200_index* idx, uint8_t num, csvb200_chunk* out, size_t out_cap, size_t* n_out)
+{
+    if (!idx || !n_out) return CSVB200_ERR_INVALID_ARG;
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    if (!idx->tape_ready) return fail(ctx, CSVB200_ERR_INVALID_STATE, "csvb200_tape_init has not been called");
+    // boundaries(record_cnt, num) (src/tape.rs:385-428); None -> StructureError::InvalidState (:99-100)
+    const uint32_t task = idx->record_cnt;
+    if (task == 0 || num == 0) return fail(ctx, CSVB200_ERR_INVALID_STATE, csvb200_status_string(CSVB200_ERR_INVALID_STATE));
+    const size_t nchunks = task < num ? 1 : num;
+    *n_out = nchunks;
+    if (!out || out_cap < nchunks) return fail(ctx, CSVB200_ERR_CAPACITY, "chunk array too small");
+    const uint32_t job = task < num ? task : task / num, rem = task < num ? 0 : task % num;
+    uint64_t acc = 0;
+    for (size_t i = 0; i < nchunks; ++i) {
+        const uint32_t len = job + (i < rem ? 1u : 0u);
+        out[i].id = (uint8_t)i;
+        out[i].start = acc * idx->jump;                       // KeyToPos(boundary.start * jump) (:104-106)
+        out[i].end = (acc + len) * idx->jump;                 // (:107-110)
+        out[i].record_cnt = len;
+        acc += len;
+    }
+    out[0].start = idx->jump;                                 // chunk 0 skips the header row (:117-123)
+    out[0].record_cnt -= 1;
+    // byte ranges the chunks delimit: two index entries per chunk, fetched in one small gather
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint64_t> slots(2 * nchunks), vals(2 * nchunks, UINT64_MAX);
+    for (size_t i = 0; i < nchunks; ++i) {
+        slots[2 * i] = out[i].start;
+        slots[2 * i + 1] = out[i].end;
+    }
+    uint64_t *d_slots = nullptr, *d_vals = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_slots, slots.size() * 8, ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_vals, slots.size() * 8, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, launch_gather_slots(idx->d_index, idx->len, d_slots, slots.size(), d_vals, ctx->stream));
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(vals.data(), d_vals, slots.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(d_slots, ctx->stream);
+    cudaFreeAsync(d_vals, ctx->stream);
+    for (size_t i = 0; i < nchunks; ++i) {
+        out[i].byte_start = vals[2 * i] == UINT64_MAX ? UINT64_MAX : vals[2 * i] + 1;
+        out[i].byte_end = vals[2 * i + 1] == UINT64_MAX ? UINT64_MAX : vals[2 * i + 1] + 1;
+    }
+    return CSVB200_OK;
+}
+
 static int seek_device(csvb200_index* idx, const uint32_t* d_rec, const uint32_t* d_fld, size_t nq,
                        csvb200_range* d_out, uint32_t* d_oob)
 {
@@ -787,6 +885,18 @@ static int seek_prepare(csvb200_index* idx)
     return CSVB200_OK;
 }
 
+static bool is_pinned(const void* p)
+{
+    cudaPointerAttributes attr{};
+    const bool ok = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return ok;
+}
+
+// Host arrays in / out.  Queries go up and ranges come down in chunks of kSeekChunk queries on two
+// streams (H2D + kernel on the context's stream, D2H on the copy stream), double buffered, so a large
+// batch costs about max(up, down) of PCIe time instead of their sum plus the kernel.  Pinned caller
+// arrays (csvb200_host_alloc) are DMA'd in place; pageable ones are staged through pinned buffers.
 static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fld, size_t nq, csvb200_range* out)
 {
     int rc = seek_prepare(idx);
@@ -794,27 +904,106 @@ static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fl
     if (nq == 0) return CSVB200_OK;
     if (!rec || !out) return fail(idx->ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     csvb200_ctx* ctx = idx->ctx;
+    constexpr size_t kSeekChunk = 1u << 20;
+    const size_t chunk = std::min(nq, kSeekChunk);
+    const size_t nchunks = (nq + chunk - 1) / chunk;
+    const int nslots = nchunks > 1 ? 2 : 1;
+    // small batches (and the scalar seeks) skip the staging allocation: the driver stages tiny pageable copies itself
+    const bool direct = nq <= 4096 || (is_pinned(rec) && is_pinned(out) && (!fld || is_pinned(fld)));
+    cudaStream_t s_up = ctx->stream, s_down = nchunks > 1 ? ctx->copy_stream : ctx->stream;
+
     uint32_t *d_rec = nullptr, *d_fld = nullptr, *d_oob = nullptr;
     csvb200_range* d_out = nullptr;
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_rec, nq * sizeof(uint32_t), ctx->stream));
-    if (fld) CU_TRY(ctx, cudaMallocAsync((void**)&d_fld, nq * sizeof(uint32_t), ctx->stream));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_out, nq * sizeof(csvb200_range), ctx->stream));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_oob, sizeof(uint32_t), ctx->stream));
-    CU_TRY(ctx, cudaMemsetAsync(d_oob, 0, sizeof(uint32_t), ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(d_rec, rec, nq * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (fld) CU_TRY(ctx, cudaMemcpyAsync(d_fld, fld, nq * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    rc = seek_device(idx, d_rec, d_fld, nq, d_out, d_oob);
+    uint8_t* h_stage = nullptr;  // per slot: [rec chunk][fld chunk][out chunk]
+    const size_t slot_bytes = chunk * (2 * sizeof(uint32_t) + sizeof(csvb200_range));
+    cudaEvent_t k_done[2] = {nullptr, nullptr}, d_done[2] = {nullptr, nullptr};
     uint32_t oob = 0;
-    if (!rc) {
-        CU_TRY(ctx, cudaMemcpyAsync(out, d_out, nq * sizeof(csvb200_range), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaMemcpyAsync(&oob, d_oob, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(s_down);
+        cudaStreamSynchronize(s_up);
+        if (d_rec) cudaFreeAsync(d_rec, s_up);
+        if (d_fld) cudaFreeAsync(d_fld, s_up);
+        if (d_out) cudaFreeAsync(d_out, s_up);
+        if (d_oob) cudaFreeAsync(d_oob, s_up);
+        if (h_stage) cudaFreeHost(h_stage);
+        for (int i = 0; i < 2; ++i) {
+            if (k_done[i]) cudaEventDestroy(k_done[i]);
+            if (d_done[i]) cudaEventDestroy(d_done[i]);
+        }
+        cudaGetLastError();
+    };
+#define SEEK_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = (expr);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            cudaGetLastError();                                                                            \
+            cleanup();                                                                                     \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? CSVB200_ERR_OOM : CSVB200_ERR_CUDA,         \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                               \
+        }                                                                                                  \
+    } while (0)
+    SEEK_TRY(cudaMallocAsync((void**)&d_rec, nslots * chunk * sizeof(uint32_t), s_up));
+    if (fld) SEEK_TRY(cudaMallocAsync((void**)&d_fld, nslots * chunk * sizeof(uint32_t), s_up));
+    SEEK_TRY(cudaMallocAsync((void**)&d_out, nslots * chunk * sizeof(csvb200_range), s_up));
+    SEEK_TRY(cudaMallocAsync((void**)&d_oob, sizeof(uint32_t), s_up));
+    SEEK_TRY(cudaMemsetAsync(d_oob, 0, sizeof(uint32_t), s_up));
+    if (!direct) SEEK_TRY(cudaHostAlloc((void**)&h_stage, nslots * slot_bytes, cudaHostAllocDefault));
+    for (int i = 0; i < nslots; ++i) {
+        SEEK_TRY(cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
+        SEEK_TRY(cudaEventCreateWithFlags(&d_done[i], cudaEventDisableTiming));
     }
-    cudaFreeAsync(d_rec, ctx->stream);
-    if (d_fld) cudaFreeAsync(d_fld, ctx->stream);
-    cudaFreeAsync(d_out, ctx->stream);
-    cudaFreeAsync(d_oob, ctx->stream);
-    if (rc) return rc;
+    auto stage_rec = [&](int slot) { return reinterpret_cast<uint32_t*>(h_stage + slot * slot_bytes); };
+    auto stage_fld = [&](int slot) { return stage_rec(slot) + chunk; };
+    auto stage_out = [&](int slot) { return reinterpret_cast<csvb200_range*>(stage_fld(slot) + chunk); };
+    // drain slot: (staged mode) wait for its D2H and hand the ranges of chunk c to the caller's array
+    auto drain = [&](size_t c) -> cudaError_t {
+        const int slot = (int)(c % nslots);
+        cudaError_t e = cudaEventSynchronize(d_done[slot]);
+        if (e == cudaSuccess && !direct) {
+            const size_t off = c * chunk, len = std::min(chunk, nq - off);
+            std::memcpy(out + off, stage_out(slot), len * sizeof(csvb200_range));
+        }
+        return e;
+    };
+    for (size_t c = 0; c < nchunks; ++c) {
+        const int slot = (int)(c % nslots);
+        const size_t off = c * chunk, len = std::min(chunk, nq - off);
+        if (c >= (size_t)nslots) {
+            if (!direct) SEEK_TRY(drain(c - nslots));                 // frees the slot's staging buffers
+            SEEK_TRY(cudaStreamWaitEvent(s_up, d_done[slot], 0));    // and its device output buffer
+        }
+        const uint32_t* src_rec = rec + off;
+        const uint32_t* src_fld = fld ? fld + off : nullptr;
+        if (!direct) {
+            std::memcpy(stage_rec(slot), src_rec, len * sizeof(uint32_t));
+            src_rec = stage_rec(slot);
+            if (fld) {
+                std::memcpy(stage_fld(slot), src_fld, len * sizeof(uint32_t));
+                src_fld = stage_fld(slot);
+            }
+        }
+        uint32_t* dr = d_rec + slot * chunk;
+        uint32_t* df = fld ? d_fld + slot * chunk : nullptr;
+        csvb200_range* dout = d_out + slot * chunk;
+        SEEK_TRY(cudaMemcpyAsync(dr, src_rec, len * sizeof(uint32_t), cudaMemcpyHostToDevice, s_up));
+        if (fld) SEEK_TRY(cudaMemcpyAsync(df, src_fld, len * sizeof(uint32_t), cudaMemcpyHostToDevice, s_up));
+        rc = seek_device(idx, dr, df, len, dout, d_oob);
+        if (rc) {
+            cleanup();
+            return rc;
+        }
+        SEEK_TRY(cudaEventRecord(k_done[slot], s_up));
+        if (s_down != s_up) SEEK_TRY(cudaStreamWaitEvent(s_down, k_done[slot], 0));
+        SEEK_TRY(cudaMemcpyAsync(direct ? out + off : stage_out(slot), dout, len * sizeof(csvb200_range),
+                                 cudaMemcpyDeviceToHost, s_down));
+        SEEK_TRY(cudaEventRecord(d_done[slot], s_down));
+    }
+    for (size_t c = nchunks > (size_t)nslots ? nchunks - nslots : 0; c < nchunks; ++c) SEEK_TRY(drain(c));
+    SEEK_TRY(cudaStreamSynchronize(s_down));
+    SEEK_TRY(cudaMemcpyAsync(&oob, d_oob, sizeof(uint32_t), cudaMemcpyDeviceToHost, s_up));
+    SEEK_TRY(cudaStreamSynchronize(s_up));
+#undef SEEK_TRY
+    cleanup();
     if (oob) return fail(ctx, CSVB200_ERR_OUT_OF_BOUNDS, "lookup slot past the end of the index");
     return CSVB200_OK;
 }
@@ -903,6 +1092,100 @@ int csvb200_gather_fields(csvb200_index* idx, const uint32_t* rec, const uint32_
     cudaFreeAsync(d_off, ctx->stream);
     cudaFreeAsync(d_out, ctx->stream);
     return CSVB200_OK;
+}
+
+// enqueue lengths + scan (+ write when d_out != nullptr) of one column on the context's stream
+static int materialize_enqueue(csvb200_index* idx, uint32_t field_idx, uint32_t first_record, uint32_t nrec, uint32_t flags,
+                               uint64_t* d_offsets, uint8_t* d_out, size_t out_cap, bool offsets_pass, bool write_pass)
+{
+    csvb200_ctx* ctx = idx->ctx;
+    MaterializeParams p{};
+    p.index = idx->d_index;
+    p.index_len = idx->len;
+    p.bytes = idx->d_bytes_owned ? idx->d_bytes_owned : idx->src;
+    p.n = idx->n;
+    p.pos_bias = idx->pos_bias;
+    p.record_cnt = idx->record_cnt;
+    p.field_cnt = idx->field_cnt;
+    p.row_size = (uint32_t)idx->jump;
+    p.field_idx = field_idx;
+    p.first_record = first_record;
+    p.nrec = nrec;
+    p.flags = flags;
+    p.offsets = d_offsets;
+    p.out = d_out;
+    p.out_cap = out_cap;
+    if (offsets_pass) {
+        const size_t sbytes = materialize_scratch_bytes(nrec);
+        int rc = ensure_scratch(ctx, sbytes);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, ctx->stream));
+        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
+        p.tile_desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
+        if (nrec == 0) CU_TRY(ctx, cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), ctx->stream));
+        CU_TRY(ctx, launch_materialize_offsets(p, ctx->stream));
+        if (nrec) ctx->launches += 1;
+    }
+    if (write_pass && nrec) {
+        CU_TRY(ctx, launch_materialize_write(p, ctx->stream));
+        ctx->launches += 1;
+    }
+    return CSVB200_OK;
+}
+
+static int materialize_prepare(csvb200_index* idx, uint32_t flags)
+{
+    int rc = seek_prepare(idx);
+    if (rc) return rc;
+    if (flags & ~(CSVB200_FIELD_UNQUOTE | CSVB200_FIELD_TRIM)) return fail(idx->ctx, CSVB200_ERR_INVALID_ARG, "unknown field flags");
+    if (!idx->d_bytes_owned && !idx->src && idx->n)
+        return fail(idx->ctx, CSVB200_ERR_INVALID_STATE, "index was built without CSVB200_BUILD_KEEP_BYTES");
+    return CSVB200_OK;
+}
+
+int csvb200_materialize_column_device(csvb200_index* idx, uint32_t field_idx, uint32_t first_record, uint32_t nrec,
+                                      uint32_t flags, uint64_t* d_offsets, uint8_t* d_out, size_t out_cap)
+{
+    int rc = materialize_prepare(idx, flags);
+    if (rc) return rc;
+    if (!d_offsets || (out_cap && !d_out)) return fail(idx->ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    return materialize_enqueue(idx, field_idx, first_record, nrec, flags, d_offsets, d_out, out_cap, true, d_out != nullptr);
+}
+
+int csvb200_materialize_column(csvb200_index* idx, uint32_t field_idx, uint32_t first_record, uint32_t nrec,
+                               uint32_t flags, uint64_t* out_offsets, uint8_t* out, size_t out_cap, size_t* out_len)
+{
+    int rc = materialize_prepare(idx, flags);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    if (!out_offsets || !out_len) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    uint64_t* d_off = nullptr;
+    uint8_t* d_out = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_off, ((size_t)nrec + 1) * sizeof(uint64_t), ctx->stream));
+    rc = materialize_enqueue(idx, field_idx, first_record, nrec, flags, d_off, nullptr, 0, true, false);
+    if (!rc) {
+        CU_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off, ((size_t)nrec + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint64_t total = out_offsets[nrec];
+        *out_len = (size_t)total;
+        if (total > out_cap) {
+            rc = fail(ctx, CSVB200_ERR_CAPACITY, "materialize destination too small");
+        } else if (total > 0) {
+            if (!out) {
+                rc = fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+            } else {
+                CU_TRY(ctx, cudaMallocAsync((void**)&d_out, total, ctx->stream));
+                rc = materialize_enqueue(idx, field_idx, first_record, nrec, flags, d_off, d_out, total, false, true);
+                if (!rc) {
+                    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                }
+            }
+        }
+    }
+    if (d_out) cudaFreeAsync(d_out, ctx->stream);
+    cudaFreeAsync(d_off, ctx->stream);
+    return rc;
 }
 
 int csvb200_block_masks(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* quote_words,

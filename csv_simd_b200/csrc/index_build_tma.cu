@@ -231,7 +231,10 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
             for (uint32_t it = 0;; ++it) {
-                // dynamic super-tile id: a tile only ever waits on tiles whose CTAs already hold a ticket
+                // dynamic super-tile id: a tile only ever waits on tiles whose CTAs already hold a ticket.
+                // (Taking the NEXT ticket early to hide the atomic's round trip measured slower, 0.423 vs
+                // 0.418 ms: a ticket held for a whole super-tile period before its loads start delays the
+                // look-back of every later tile.)
                 uint32_t tile = atomicAdd(p.ticket, 1u);
                 if (tile >= p.num_tiles) tile = kInvalidTile;
 #pragma unroll
@@ -476,7 +479,6 @@ cudaError_t launch_index_build_tma(const BuildParams& p_in, cudaStream_t stream)
         grid_cap = sms * per_sm;   // persistent: one resident CTA per slot (2 per SM by design)
     }
     unsigned grid = (unsigned)(p.num_tiles < (uint32_t)grid_cap ? p.num_tiles : (uint32_t)grid_cap);
-    if (p.tune >= 8u && grid < 2u) grid = 2u;   // scanner mode: CTA 0 scans, the others take tiles
     index_build_tma_kernel<<<grid, kTmaThreads, sizeof(SmemTma), stream>>>(p, tmap);
     return cudaGetLastError();
 }

@@ -100,4 +100,40 @@ cudaError_t launch_gather_bytes(const uint8_t* bytes, const uint64_t* ranges, co
                                 uint8_t* out, cudaStream_t stream);
 cudaError_t launch_range_lengths(const uint64_t* ranges, uint64_t nq, uint64_t* lens, cudaStream_t stream);
 
+// K5 tape validation (tape.cu): first index slot whose separator class does not fit its place in the record
+struct TapeValidateParams {
+    const uint64_t* index;
+    uint64_t index_len;
+    const uint8_t* bytes;    // the shard the index positions refer to
+    uint64_t n;
+    uint64_t pos_bias;       // global offset of bytes[0] (index positions are global)
+    uint64_t jump;
+    int crlf;
+    uint64_t* first_bad_slot;   // device word, preset to UINT64_MAX; atomicMin
+};
+cudaError_t launch_tape_validate(const TapeValidateParams& p, cudaStream_t stream);
+// out[i] = index[slots[i]] (UINT64_MAX when the slot is past the end)
+cudaError_t launch_gather_slots(const uint64_t* index, uint64_t index_len, const uint64_t* slots, uint64_t n,
+                                uint64_t* out, cudaStream_t stream);
+
+// K6 column materialisation (materialize.cu)
+struct MaterializeParams {
+    const uint64_t* index;
+    uint64_t index_len;
+    const uint8_t* bytes;
+    uint64_t n;
+    uint64_t pos_bias;
+    uint32_t record_cnt, field_cnt, row_size;
+    uint32_t field_idx, first_record, nrec;
+    uint32_t flags;          // 1 = unquote, 2 = trim
+    uint64_t* offsets;       // [nrec + 1] exclusive prefix sums of the value lengths
+    uint8_t* out;
+    uint64_t out_cap;
+    uint64_t* tile_desc;     // look-back descriptors (zeroed), materialize_scratch_bytes(nrec) - 128 bytes
+    uint32_t* ticket;        // zeroed
+};
+size_t materialize_scratch_bytes(uint32_t nrec);   // [128 B ticket cell][descriptors]
+cudaError_t launch_materialize_offsets(const MaterializeParams& p, cudaStream_t stream);
+cudaError_t launch_materialize_write(const MaterializeParams& p, cudaStream_t stream);
+
 }  // namespace csvb200

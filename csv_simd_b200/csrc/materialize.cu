@@ -1,0 +1,189 @@
+// materialize.cu -- K6: column materialisation.
+//
+// RecordSource::seek_field (src/record_source.rs:104-140) hands back the RAW slice of a field,
+// "incl. surrounding quotes / padding; no unescape, no trim" (:135-139).  What callers do next is turn
+// a column of such slices into values; this file does that on the device for a whole column at once:
+//   for r in [first_record, first_record + nrec):   (start, end) = seek_field(r, field_idx)
+//       value = raw slice, optionally trimmed of ASCII space / tab, optionally RFC-4180 unquoted
+//               (outer quotes stripped when both are present, "" -> ")
+//   offsets[r - first_record] = exclusive prefix sum of the value lengths, out = values back to back
+// Two kernels: (1) lengths + exclusive scan fused (one pass, decoupled look-back over 62-bit sums),
+// (2) the write.  Both read two index entries per record and the field's bytes: HBM sector-bound.
+#include "internal.h"
+
+namespace csvb200 {
+
+namespace {
+
+constexpr int kMatThreads = 256;
+constexpr int kMatItems = 4;
+constexpr int kMatTile = kMatThreads * kMatItems;
+constexpr uint64_t kMatAgg = 1ull << 62, kMatPrefix = 2ull << 62, kMatMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t ldg_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_relaxed(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// seek_field (src/record_source.rs:104-140) as byte offsets relative to p.bytes; false = Ok(None) or a
+// slot the reference would panic on
+__device__ __forceinline__ bool field_range(const MaterializeParams& p, uint32_t r, uint64_t& a, uint64_t& b)
+{
+    if ((uint32_t)(r + 1u) >= p.record_cnt || p.field_idx >= p.field_cnt) return false;
+    const uint32_t s = (uint32_t)(r + 1u) * p.row_size + p.field_idx;   // u32 arithmetic, as the reference
+    if ((uint64_t)s + 1 >= p.index_len) return false;
+    a = ldg_u64(p.index + s) + 1 - p.pos_bias;
+    b = ldg_u64(p.index + s + 1) - p.pos_bias;
+    return a <= b && b <= p.n;
+}
+
+// trims [a, b) in place and reports whether the value is a quoted field to unquote
+__device__ __forceinline__ bool trim_and_test(const MaterializeParams& p, uint64_t& a, uint64_t& b)
+{
+    const uint8_t* x = p.bytes;
+    if (p.flags & 2u) {
+        while (a < b && (x[a] == 0x20u || x[a] == 0x09u)) ++a;
+        while (b > a && (x[b - 1] == 0x20u || x[b - 1] == 0x09u)) --b;
+    }
+    if ((p.flags & 1u) && b - a >= 2 && x[a] == 0x22u && x[b - 1] == 0x22u) {
+        ++a;
+        --b;
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ uint64_t value_len(const MaterializeParams& p, uint32_t r)
+{
+    uint64_t a, b;
+    if (!field_range(p, r, a, b)) return 0;
+    if (!trim_and_test(p, a, b)) return b - a;
+    uint64_t o = 0;
+    const uint8_t* x = p.bytes;
+    while (a < b) {
+        if (x[a] == 0x22u && a + 1 < b && x[a + 1] == 0x22u) ++a;
+        ++o;
+        ++a;
+    }
+    return o;
+}
+
+__global__ void __launch_bounds__(kMatThreads) materialize_offsets_kernel(const MaterializeParams p)
+{
+    __shared__ uint64_t s_warp[kMatThreads / 32];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_tile;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);   // tiles are taken in order: look-back only waits on started tiles
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t i0 = (uint64_t)tile * kMatTile + (uint64_t)tid * kMatItems;
+    uint64_t len[kMatItems], tsum = 0;
+#pragma unroll
+    for (int k = 0; k < kMatItems; ++k) {
+        len[k] = i0 + k < p.nrec ? value_len(p, p.first_record + (uint32_t)(i0 + k)) : 0;
+        tsum += len[k];
+    }
+    // block exclusive scan of the thread sums
+    uint64_t inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint64_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kMatThreads / 32; ++w) {
+        if (w < (int)warp) wbase += s_warp[w];
+        total += s_warp[w];
+    }
+    // decoupled look-back over the tile totals (status in the top two bits)
+    if (tid == 0) {
+        st_relaxed(p.tile_desc + tile, kMatAgg | (total & kMatMask));
+        uint64_t prefix = 0;
+        for (int64_t t = (int64_t)tile - 1; t >= 0;) {
+            const uint64_t d = ld_relaxed(p.tile_desc + t);
+            const uint64_t st = d >> 62;
+            if (st == 0) {
+                __nanosleep(40);
+                continue;
+            }
+            prefix += d & kMatMask;
+            if (st == 2) break;
+            --t;
+        }
+        st_relaxed(p.tile_desc + tile, kMatPrefix | ((prefix + total) & kMatMask));
+        s_prefix = prefix;
+    }
+    __syncthreads();
+    uint64_t off = s_prefix + wbase + (inc - tsum);
+#pragma unroll
+    for (int k = 0; k < kMatItems; ++k) {
+        if (i0 + k < p.nrec) p.offsets[i0 + k] = off;
+        off += len[k];
+    }
+    if (i0 < p.nrec && i0 + kMatItems >= p.nrec) p.offsets[p.nrec] = off;   // the thread owning the last record
+}
+
+__global__ void __launch_bounds__(kMatThreads) materialize_write_kernel(const MaterializeParams p)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint8_t* x = p.bytes;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nrec; i += stride) {
+        uint64_t a, b;
+        if (!field_range(p, p.first_record + (uint32_t)i, a, b)) continue;
+        uint64_t o = p.offsets[i];
+        const uint64_t o_end = p.offsets[i + 1];
+        if (o_end > p.out_cap) continue;   // host form checks the capacity first; device form clips whole values
+        if (!trim_and_test(p, a, b)) {
+            for (; a < b; ++a) p.out[o++] = x[a];
+        } else {
+            while (a < b) {
+                if (x[a] == 0x22u && a + 1 < b && x[a + 1] == 0x22u) ++a;
+                p.out[o++] = x[a];
+                ++a;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+size_t materialize_scratch_bytes(uint32_t nrec) { return 128 + ((size_t)(nrec + kMatTile - 1) / kMatTile + 1) * sizeof(uint64_t); }
+
+cudaError_t launch_materialize_offsets(const MaterializeParams& p, cudaStream_t stream)
+{
+    const uint32_t tiles = (p.nrec + kMatTile - 1) / kMatTile;
+    if (tiles == 0) return cudaSuccess;
+    materialize_offsets_kernel<<<tiles, kMatThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_materialize_write(const MaterializeParams& p, cudaStream_t stream)
+{
+    if (p.nrec == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t blocks = ((uint64_t)p.nrec + kMatThreads - 1) / kMatThreads;
+    const uint64_t max_blocks = (uint64_t)sms * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    materialize_write_kernel<<<(unsigned)blocks, kMatThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace csvb200

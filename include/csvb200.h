@@ -155,6 +155,37 @@ void csvb200_index_free(csvb200_index* idx);
  * as TapeCore::record_jump_size, src/tape.rs:200-201). */
 int csvb200_tape_init(csvb200_index* idx, uint32_t field_cnt, int crlf, uint32_t* record_cnt, uint64_t* jump);
 
+/* Device-side validation of what the seeks assume (beyond the reference, which only tests
+ * (len-1) % jump): entry s >= 1 is the k-th separator of its record, k = (s-1) % jump, and must be
+ * ',' for the field separators and the line end (CR or LF; CR then the adjacent LF for CRLF files) in
+ * the last slot(s).  Reports the first slot that is not, i.e. the first ragged / malformed record.
+ * Needs the input bytes (CSVB200_BUILD_KEEP_BYTES, or a device-built index whose input is still alive). */
+typedef struct csvb200_tape_report {
+    uint64_t index_len;
+    uint64_t jump;
+    uint64_t problem;          /* (len-1) % jump, src/tape.rs:327 */
+    uint64_t first_bad_slot;   /* UINT64_MAX: every entry has the class its slot requires */
+    uint64_t first_bad_record; /* row (0 = header) containing it; the trailing partial row when only problem != 0 */
+    uint64_t first_bad_pos;    /* byte offset of the offending separator */
+    uint32_t record_cnt;       /* (len-1) / jump, src/tape.rs:323-325 */
+    uint32_t ok;               /* first_bad_slot == UINT64_MAX && problem == 0 */
+} csvb200_tape_report;
+int csvb200_tape_validate(csvb200_index* idx, uint32_t field_cnt, int crlf, csvb200_tape_report* out);
+
+/* Tape::chunks(num) (src/tape.rs:95-140) over boundaries(record_cnt, num) (src/tape.rs:385-428): slot
+ * ranges of `num` near-equal runs of rows (chunk 0 skips the header row), plus the byte range each run
+ * occupies in the input ([byte_start, byte_end), through its last line end) for downstream consumers.
+ * record_cnt == 0 or num == 0 -> CSVB200_ERR_INVALID_STATE; fewer rows than chunks -> one chunk. */
+typedef struct csvb200_chunk {
+    uint64_t start;      /* KeyToPos of the chunk's first row (slot of the separator that precedes it) */
+    uint64_t end;        /* KeyToPos one row past its last row */
+    uint64_t byte_start; /* index[start] + 1 */
+    uint64_t byte_end;   /* index[end] + 1 */
+    uint32_t record_cnt;
+    uint8_t id;
+} csvb200_chunk;
+int csvb200_tape_chunks(csvb200_index* idx, uint8_t num, csvb200_chunk* out, size_t out_cap, size_t* n_out);
+
 /* ---- lookups: RecordSource (src/record_source.rs:70-140) ----------------------------------- */
 /* scalar: *found = 0 means Ok(None) */
 int csvb200_seek_record(csvb200_index* idx, uint32_t record_idx, csvb200_range* out, int* found);
@@ -170,6 +201,24 @@ int csvb200_seek_records_device(csvb200_index* idx, const uint32_t* d_rec, size_
  * exclusive prefix sums of the lengths, out receives the packed bytes (out_cap bytes). */
 int csvb200_gather_fields(csvb200_index* idx, const uint32_t* rec, const uint32_t* fld, size_t nq,
                           uint64_t* out_offsets, uint8_t* out, size_t out_cap);
+
+/* ---- column materialisation (beyond the reference: seek_field returns the RAW slice incl. quotes and
+ * padding, src/record_source.rs:135-139) ----------------------------------------------------------- */
+/* The values of field `field_idx` of records [first_record, first_record + nrec) (numbered as in
+ * seek_field: 0 = first row after the header), packed back to back; out_offsets[nrec + 1] are the
+ * exclusive prefix sums of their lengths.  A record seek_field reports as None contributes an empty
+ * value.  flags: TRIM strips ASCII space / tab at both ends, then UNQUOTE strips the outer quotes when
+ * both are present and turns every "" into ".  Needs the input bytes (CSVB200_BUILD_KEEP_BYTES).
+ * Host form: *out_len receives the total; CSVB200_ERR_CAPACITY (offsets and *out_len valid) when
+ * out_cap is too small.  Device form: asynchronous on the context's stream, d_out may be NULL to get
+ * the offsets only; values that would end past out_cap are skipped. */
+#define CSVB200_FIELD_RAW 0u
+#define CSVB200_FIELD_UNQUOTE 1u
+#define CSVB200_FIELD_TRIM 2u
+int csvb200_materialize_column(csvb200_index* idx, uint32_t field_idx, uint32_t first_record, uint32_t nrec,
+                               uint32_t flags, uint64_t* out_offsets, uint8_t* out, size_t out_cap, size_t* out_len);
+int csvb200_materialize_column_device(csvb200_index* idx, uint32_t field_idx, uint32_t first_record, uint32_t nrec,
+                                      uint32_t flags, uint64_t* d_offsets, uint8_t* d_out, size_t out_cap);
 
 /* ---- K1 known-answer exports (debug) -------------------------------------------------------- */
 /* per 64-byte block: quote_bits / all_struct as get_struct_positions(16 | 3) (src/avx/stage1.rs:392,394) */

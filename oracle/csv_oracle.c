@@ -523,4 +523,56 @@ int oracle_chunks(uint32_t record_cnt, uint64_t jump, uint8_t num, oracle_chunk 
 }
 
 /* src/lib.rs:139-152 blsr identity: x & (x - 1) clears the lowest set bit. */
+/* ---- definitions BEYOND the reference (SURVEY 8f "next" rows) -------------------------------------
+ * The reference has no counterpart for these, so there is nothing to pin them to: they are scalar
+ * statements of the definitions in include/csvb200.h, used to check the CUDA kernels.  "parity unpinned". */
+
+/* csvb200_tape_validate: first slot s >= 1 whose separator does not fit k = (s-1) % jump. */
+uint64_t oracle_tape_first_bad_slot(const uint8_t *bytes, size_t n, const uint64_t *index,
+                                    size_t index_len, uint32_t field_cnt, int crlf)
+{
+    const uint64_t jump = crlf ? (uint64_t)field_cnt + 1 : (uint64_t)field_cnt;
+    for (size_t s = 1; s < index_len; ++s) {
+        const uint64_t k = (s - 1) % jump, pos = index[s];
+        int ok = pos < n;
+        if (ok) {
+            const uint8_t b = bytes[pos];
+            if (crlf) {
+                if (k + 2 < jump) ok = b == ',';
+                else if (k + 2 == jump) ok = b == '\r';
+                else ok = b == '\n' && index[s - 1] + 1 == pos;
+            } else {
+                ok = k + 1 < jump ? b == ',' : (b == '\n' || b == '\r');
+            }
+        }
+        if (!ok) return s;
+    }
+    return UINT64_MAX;
+}
+
+/* csvb200_materialize_*: the value of a raw field slice (src/record_source.rs:135-139 returns the raw
+ * slice) after optional trim (ASCII space / tab at both ends) and optional RFC-4180 unquoting (outer
+ * quotes stripped when both present, "" -> ").  Returns the length; writes to out when non-null. */
+size_t oracle_field_value(const uint8_t *raw, size_t len, uint32_t flags, uint8_t *out)
+{
+    size_t a = 0, b = len, o = 0;
+    if (flags & 2u) {
+        while (a < b && (raw[a] == ' ' || raw[a] == '\t')) ++a;
+        while (b > a && (raw[b - 1] == ' ' || raw[b - 1] == '\t')) --b;
+    }
+    if ((flags & 1u) && b - a >= 2 && raw[a] == '"' && raw[b - 1] == '"') {
+        ++a;
+        --b;
+        while (a < b) {
+            if (raw[a] == '"' && a + 1 < b && raw[a + 1] == '"') ++a;
+            if (out) out[o] = raw[a];
+            ++o;
+            ++a;
+        }
+        return o;
+    }
+    if (out) memcpy(out, raw + a, b - a);
+    return b - a;
+}
+
 uint64_t oracle_blsr(uint64_t x) { return x & (x ? x - 1 : 0); }

@@ -88,6 +88,10 @@ def lib():
                                                C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p]
         L.oracle_boundaries.argtypes = [C.c_uint32, C.c_uint8, C.POINTER(_Boundary)]
         L.oracle_chunks.argtypes = [C.c_uint32, C.c_uint64, C.c_uint8, C.POINTER(_Chunk)]
+        L.oracle_tape_first_bad_slot.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
+        L.oracle_tape_first_bad_slot.restype = C.c_uint64
+        L.oracle_field_value.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+        L.oracle_field_value.restype = C.c_size_t
         L.oracle_blsr.argtypes = [C.c_uint64]
         L.oracle_blsr.restype = C.c_uint64
         _lib = L
@@ -240,6 +244,36 @@ def chunks(record_cnt: int, jump: int, num: int):
         return None
     return [dict(id=out[i].id, start=out[i].start, end=out[i].end, record_cnt=out[i].record_cnt)
             for i in range(n)]
+
+
+# ---- definitions beyond the reference: see csv_oracle.c -----------------------------
+def tape_first_bad_slot(data, index: np.ndarray, field_cnt: int, crlf: bool) -> int:
+    a = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+    index = np.ascontiguousarray(index, dtype=np.uint64)
+    return int(lib().oracle_tape_first_bad_slot(a.ctypes.data, a.size, index.ctypes.data, index.size, field_cnt,
+                                                int(crlf)))
+
+
+def field_value(raw: bytes, flags: int) -> bytes:
+    buf = np.frombuffer(raw, dtype=np.uint8) if len(raw) else np.zeros(1, dtype=np.uint8)
+    out = np.zeros(max(len(raw), 1), dtype=np.uint8)
+    n = lib().oracle_field_value(buf.ctypes.data, len(raw), flags, out.ctypes.data)
+    return out[:n].tobytes()
+
+
+def materialize_column(data, index: np.ndarray, record_cnt: int, field_cnt: int, crlf: bool, field_idx: int,
+                       first_record: int, nrec: int, flags: int):
+    """(offsets[nrec+1], packed bytes): field `field_idx` of records first_record .. +nrec through the
+    seek_field restatement (a record that seek_field reports as None contributes an empty value)."""
+    raw = data if isinstance(data, (bytes, bytearray)) else np.asarray(data, dtype=np.uint8).tobytes()
+    offs, parts, acc = [0], [], 0
+    for r in range(first_record, first_record + nrec):
+        rg = seek_field(index, len(raw), record_cnt, field_cnt, crlf, r, field_idx)
+        v = field_value(raw[rg[0]:rg[1]], flags) if rg is not None and rg[1] >= rg[0] else b""
+        parts.append(v)
+        acc += len(v)
+        offs.append(acc)
+    return np.array(offs, dtype=np.uint64), b"".join(parts)
 
 
 def blsr(x: int) -> int:

@@ -479,3 +479,134 @@ def test_build_to_host_pipeline_multi_chunk(ctx):
     ln = ctx.index_build_to_host(dense.ctypes.data, dense.size, out.ctypes.data, out.size)
     assert ln == dense.size + 1 and out[1] == 0 and out[ln - 1] == dense.size - 1
     assert (np.diff(out[1:ln].astype(np.int64)) == 1).all()
+
+
+# ---- SURVEY 8f "next" rows: device-side tape validation, chunks with byte ranges, column materialisation ----
+def _ragged(kind):
+    rows = [b"c0,c1,c2"] + [b"%d,%d,%d" % (i, i * 7, i * 13) for i in range(5000)]
+    nl = b"\r\n" if kind == "crlf" else b"\n"
+    return rows, nl
+
+
+@pytest.mark.parametrize("kind", ["lf", "crlf"])
+def test_tape_validate_vs_oracle(ctx, kind):
+    rows, nl = _ragged(kind)
+    crlf = kind == "crlf"
+    good = nl.join(rows) + nl
+    idx = ctx.index_build(good, cs.BUILD_KEEP_BYTES)
+    rep = idx.tape_validate(3, crlf)
+    assert rep["ok"] == 1 and rep["first_bad_slot"] == U64MAX and rep["problem"] == 0
+    assert rep["record_cnt"] == len(rows) and rep["jump"] == (4 if crlf else 3)
+    assert O.tape_first_bad_slot(good, idx.to_host(), 3, crlf) == U64MAX
+    idx.free()
+    # ragged rows whose separator counts cancel: the reference's (len-1) % jump test passes, the seeks go wrong
+    bad_rows = list(rows)
+    bad_rows[1234] = b"1,2"            # one field short ...
+    bad_rows[4000] = b"1,2,3,4"        # ... one field long
+    for data in (nl.join(bad_rows) + nl, nl.join(rows[:777] + [b"x"] + rows[777:]) + nl,
+                 nl.join(rows) + nl + b"7,8", good.replace(b"10,70,130" + nl, b"10,70,130" + (b"\n" if crlf else b"\r\n"), 1)):
+        idx = ctx.index_build(data, cs.BUILD_KEEP_BYTES)
+        host = idx.to_host()
+        rep = idx.tape_validate(3, crlf)
+        want = O.tape_first_bad_slot(data, host, 3, crlf)
+        assert rep["first_bad_slot"] == want
+        jump = 4 if crlf else 3
+        assert rep["problem"] == (host.size - 1) % jump and rep["record_cnt"] == (host.size - 1) // jump
+        if want != U64MAX:
+            assert rep["ok"] == 0 and rep["first_bad_record"] == (want - 1) // jump and rep["first_bad_pos"] == host[want]
+        else:
+            assert rep["ok"] == (1 if rep["problem"] == 0 else 0)
+        idx.free()
+    # without the bytes the call must refuse, not guess
+    idx = ctx.index_build(good)
+    with pytest.raises(cs.InvalidState):
+        idx.tape_validate(3, crlf)
+    idx.free()
+
+
+def test_tape_validate_large_random(ctx):
+    data, rows = gen.unquoted(8 << 20, seed=9)
+    raw = bytearray(data.tobytes())
+    idx = ctx.index_build(bytes(raw), cs.BUILD_KEEP_BYTES)
+    assert idx.tape_validate(16, False)["ok"] == 1
+    host = idx.to_host()
+    idx.free()
+    rng = np.random.default_rng(3)
+    for _ in range(4):
+        s = int(rng.integers(1, host.size))
+        pos = int(host[s])
+        old = raw[pos]
+        raw[pos] = 0x0A if old == 0x2C else 0x2C       # swap the class of one separator
+        idx = ctx.index_build(bytes(raw), cs.BUILD_KEEP_BYTES)
+        rep = idx.tape_validate(16, False)
+        assert rep["first_bad_slot"] == s == O.tape_first_bad_slot(bytes(raw), idx.to_host(), 16, False)
+        idx.free()
+        raw[pos] = old
+
+
+def test_tape_chunks_vs_oracle(ctx):
+    for name, fc, crlf in (("sample.csv", 3, False), ("sample_rx.csv", 8, True)):
+        raw = golden_bytes(name)
+        idx = ctx.index_build(raw)
+        with pytest.raises(cs.InvalidState):
+            idx.tape_chunks(3)                       # before tape_init
+        rc, jump = idx.tape_init(fc, crlf)
+        host = idx.to_host()
+        for num in (1, 2, 3, 5, 12, 200):
+            got = idx.tape_chunks(num)
+            want = O.chunks(rc, jump, num)
+            assert [(c["id"], c["start"], c["end"], c["record_cnt"]) for c in got] == \
+                   [(c["id"], c["start"], c["end"], c["record_cnt"]) for c in want]
+            for c in got:
+                assert c["byte_start"] == int(host[c["start"]]) + 1 and c["byte_end"] == int(host[c["end"]]) + 1
+                if c["record_cnt"]:
+                    seg = raw[c["byte_start"]:c["byte_end"]]
+                    assert seg.endswith(b"\n") and seg.count(b"\n") >= c["record_cnt"]
+            assert got[-1]["byte_end"] == len(raw)
+        with pytest.raises(cs.InvalidState):
+            idx.tape_chunks(0)
+        idx.free()
+
+
+def _column_cases():
+    rows = [b'id,name,note']
+    vals = [b'plain', b'"quoted"', b'  padded\t', b'"with ""escapes"" inside"', b'""', b'"', b'', b' "q, and\nnewline" ',
+            b'"a""', b'""""', b'x"y', b'"tail""', b'\t\t', b'" "']
+    for i in range(3000):
+        rows.append(b"%d,%s,%s" % (i, vals[i % len(vals)], vals[(i * 5 + 3) % len(vals)]))
+    return b"\n".join(rows) + b"\n"
+
+
+@pytest.mark.parametrize("flags", [0, 1, 2, 3])
+def test_materialize_column_vs_oracle(ctx, flags):
+    raw = _column_cases()
+    idx = ctx.index_build(raw, cs.BUILD_KEEP_BYTES)
+    rc, jump = idx.tape_init(3, False)
+    host = idx.to_host()
+    for fld, first, nrec in ((1, 0, rc - 1), (2, 0, rc - 1), (0, 17, 1000), (1, rc - 5, 20), (2, 5, 0), (7, 0, 10), (1, 1024, 1024)):
+        offs, out = idx.materialize_column(fld, first, nrec, flags)
+        w_offs, w_out = O.materialize_column(raw, host, rc, 3, False, fld, first, nrec, flags)
+        assert (offs == w_offs).all(), (fld, first, nrec)
+        assert out.tobytes() == w_out, (fld, first, nrec)
+    idx.free()
+
+
+def test_materialize_column_crlf_and_device_form(ctx):
+    import torch
+    raw = golden_bytes("sample_rx.csv")
+    idx = ctx.index_build(raw, cs.BUILD_KEEP_BYTES)
+    rc, jump = idx.tape_init(8, True)
+    host = idx.to_host()
+    dev = torch.device("cuda", ctx.device)
+    for fld in range(8):
+        offs, out = idx.materialize_column(fld, 0, rc - 1, cs.FIELD_UNQUOTE | cs.FIELD_TRIM)
+        w_offs, w_out = O.materialize_column(raw, host, rc, 8, True, fld, 0, rc - 1, 3)
+        assert (offs == w_offs).all() and out.tobytes() == w_out
+        d_off = torch.zeros(rc, dtype=torch.int64, device=dev)
+        d_out = torch.zeros(max(len(w_out), 1), dtype=torch.uint8, device=dev)
+        idx.materialize_column_device(fld, 0, rc - 1, 3, d_off.data_ptr(), d_out.data_ptr(), len(w_out))
+        torch.cuda.synchronize()
+        assert (d_off.cpu().numpy().view(np.uint64) == w_offs).all()
+        assert d_out.cpu().numpy()[:len(w_out)].tobytes() == w_out
+    assert idx.materialize_column(2, 1, 1, 3)[1].tobytes() == b"INTERNAL MED, CARD. ELECTROPHYSIOLOGY"
+    idx.free()

@@ -134,3 +134,34 @@ def test_chunks_restatement():
     ch = O.chunks(15, 3, 4)
     assert [c["record_cnt"] for c in ch] == [3, 4, 4, 3] and ch[0]["start"] == 3 and ch[-1]["end"] == 45
     assert O.chunks(0, 3, 4) is None
+
+
+# ---- definitions beyond the reference: known answers of the scalar statements --------
+def test_field_value_known_answers():
+    U, T = 1, 2
+    cases_ = [
+        (b'plain', 0, b'plain'), (b'"quoted"', U, b'quoted'), (b'"quoted"', 0, b'"quoted"'),
+        (b'  padded\t', T, b'padded'), (b'  padded\t', U, b'  padded\t'),
+        (b'"with ""escapes"" inside"', U, b'with "escapes" inside'), (b'""', U, b''), (b'"', U, b'"'),
+        (b'', U | T, b''), (b' "q, and\nnewline" ', U | T, b'q, and\nnewline'), (b' "x" ', U, b' "x" '),
+        (b'""""', U, b'"'), (b'"a"""', U, b'a"'), (b'x"y', U, b'x"y'), (b'"a"b"', U, b'a"b'), (b'\t \t', T, b''),
+        (b'" "', U | T, b' '),
+    ]
+    for raw, flags, want in cases_:
+        assert O.field_value(raw, flags) == want, (raw, flags)
+
+
+def test_tape_first_bad_slot_known_answers():
+    d = b"a,b\n1,2\n3\n4,5\n"
+    idx = O.closed_form_numpy(d)
+    assert O.tape_first_bad_slot(d, idx, 2, False) == 5            # the '\n' after "3" sits in a ',' slot
+    good = b"a,b\r\n1,2\r\n"
+    assert O.tape_first_bad_slot(good, O.closed_form_numpy(good), 2, True) == 0xFFFFFFFFFFFFFFFF
+    lone = b"a,b\r\n1,2\n\n"                                      # LF LF where CR LF is required
+    assert O.tape_first_bad_slot(lone, O.closed_form_numpy(lone), 2, True) == 5
+    for name, fc, crlf in (("sample.csv", 3, False), ("sample_rx.csv", 8, True)):
+        from tests.conftest import golden_bytes
+        raw = golden_bytes(name)
+        assert O.tape_first_bad_slot(raw, O.read_sse(raw), fc, crlf) == 0xFFFFFFFFFFFFFFFF
+    raw = golden_bytes("reader_test01.csv")                        # ragged last row
+    assert O.tape_first_bad_slot(raw, O.read_sse(raw), 3, False) != 0xFFFFFFFFFFFFFFFF
