@@ -23,6 +23,15 @@ class Range(C.Structure):
     _fields_ = [("start", C.c_uint64), ("end", C.c_uint64)]
 
 
+class StreamStats(C.Structure):
+    _fields_ = [("bytes", C.c_uint64), ("entries", C.c_uint64), ("seconds", C.c_double), ("chunks", C.c_uint32),
+                ("end_parity", C.c_int)]
+
+
+READ_FN = C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint64)
+
+
 class TapeReport(C.Structure):
     _fields_ = [("index_len", C.c_uint64), ("jump", C.c_uint64), ("problem", C.c_uint64),
                 ("first_bad_slot", C.c_uint64), ("first_bad_record", C.c_uint64), ("first_bad_pos", C.c_uint64),
@@ -50,6 +59,10 @@ SIGNATURES = {
     "csvb200_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, vpp]),
     "csvb200_index_build_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, vpp]),
     "csvb200_index_build_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, szp]),
+    "csvb200_index_build_stream": (C.c_int, [C.c_void_p, READ_FN, C.c_void_p, SINK_FN, C.c_void_p, C.c_size_t,
+                                             C.POINTER(StreamStats)]),
+    "csvb200_index_build_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, szp,
+                                           C.POINTER(StreamStats)]),
     "csvb200_shard_quote_parity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u32p]),
     "csvb200_index_build_shard_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64,
                                                    C.c_int, vpp]),

@@ -108,6 +108,64 @@ class Context:
                                                           dst_cap, C.byref(ln)))
         return ln.value
 
+    # -- streaming ingest -------------------------------------------------------------------
+    def index_build_stream(self, read, sink, chunk_bytes: int = 0) -> dict:
+        """csvb200_index_build_stream: read(cap) -> bytes-like (b"" = end of input); sink(entries: np.ndarray
+        of u64 (a view, copy it to keep it), first_slot: int).  Returns the stream stats."""
+        err = []
+
+        def _read(_user, dst, cap):
+            try:
+                b = read(cap)
+                k = len(b)
+                if k:
+                    C.memmove(dst, bytes(b) if not isinstance(b, (bytes, bytearray)) else b, k)
+                return k
+            except BaseException as e:  # never unwind through the C frames
+                err.append(e)
+                return 0
+
+        def _sink(_user, entries, count, first):
+            try:
+                sink(np.ctypeslib.as_array(entries, shape=(count,)), int(first))
+                return 0
+            except BaseException as e:
+                err.append(e)
+                return 1
+
+        st = _lib.StreamStats()
+        rc = self._lib.csvb200_index_build_stream(self._h, _lib.READ_FN(_read), None, _lib.SINK_FN(_sink), None,
+                                                  chunk_bytes, C.byref(st))
+        if err:
+            raise err[0]
+        self._check(rc)
+        return {k: getattr(st, k) for k, _ in _lib.StreamStats._fields_}
+
+    def index_build_file(self, path: str, out: np.ndarray | None = None):
+        """csvb200_index_build_file: file -> host index (u64 array).  Returns (index, stats)."""
+        import os
+        st = _lib.StreamStats()
+        ln = C.c_size_t()
+        if out is None:
+            size = os.path.getsize(path) if os.path.exists(path) else 0
+            out = np.empty(size // 3 + 4096, dtype=np.uint64)
+        rc = self._lib.csvb200_index_build_file(self._h, os.fsencode(path), out.ctypes.data, out.size, C.byref(ln),
+                                                C.byref(st))
+        if rc == 9 and ln.value > out.size:   # denser than the reserve: the count is known now
+            out = np.empty(ln.value, dtype=np.uint64)
+            rc = self._lib.csvb200_index_build_file(self._h, os.fsencode(path), out.ctypes.data, out.size,
+                                                    C.byref(ln), C.byref(st))
+        self._check(rc)
+        return out[:ln.value], {k: getattr(st, k) for k, _ in _lib.StreamStats._fields_}
+
+    def index_build_file_ptr(self, path: str, dst_ptr: int, dst_cap: int):
+        import os
+        st = _lib.StreamStats()
+        ln = C.c_size_t()
+        self._check(self._lib.csvb200_index_build_file(self._h, os.fsencode(path), C.c_void_p(dst_ptr), dst_cap,
+                                                       C.byref(ln), C.byref(st)))
+        return ln.value, {k: getattr(st, k) for k, _ in _lib.StreamStats._fields_}
+
     def shard_quote_parity(self, dev_ptr: int, n: int) -> int:
         p = C.c_uint32()
         self._check(self._lib.csvb200_shard_quote_parity(self._h, C.c_void_p(dev_ptr), n, C.byref(p)))

@@ -12,73 +12,11 @@
 #include <string>
 #include <vector>
 
-#include "../../include/csvb200.h"
-#include "internal.h"
+#include "ctx.h"
 
 using namespace csvb200;
 
-namespace {
-constexpr size_t kCells = 4096;              // result cells (4 x u64 each): a ring of kRingCells + one scratch cell
-constexpr size_t kCellWords = 4;
-constexpr size_t kRingCells = kCells - 1;    // the last cell is the out-of-bounds flag of the async seek calls
-constexpr uint64_t kDefaultPredictWindow = 64u << 10;
-constexpr size_t kStageBytes = 32u << 20;    // pinned staging buffers for pageable input
-constexpr int kStageBufs = 2;
-constexpr size_t kE2eChunk = 64u << 20;      // H2D / kernel / D2H pipeline granularity
-}  // namespace
-
-struct csvb200_ctx {
-    int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // D2H of finished index segments (overlaps H2D)
-    cudaStream_t stream = nullptr;       // the stream work is issued on
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
-    bool timed = false;
-    uint8_t* d_scratch = nullptr;  // [16 B ticket cell][look-back descriptors]
-    size_t scratch_bytes = 0;
-    uint64_t* d_cells = nullptr;
-    uint64_t* h_cells = nullptr;
-    size_t next_cell = 0;
-    uint8_t* h_stage[kStageBufs] = {nullptr, nullptr};
-    cudaEvent_t stage_free[kStageBufs] = {nullptr, nullptr};
-    uint32_t reserve_num = 1, reserve_den = 3;
-    uint64_t launches = 0;
-    int kernel_override = 0;  // 0 = auto, 1 = simple, 2 = tma (CSVB200_KERNEL)
-    uint32_t tune = 0;        // CSVB200_TUNE experiment knob
-    std::string err;
-};
-
-struct csvb200_index {
-    csvb200_ctx* ctx = nullptr;
-    uint64_t* d_index = nullptr;
-    size_t cap = 0;
-    size_t len = 0;
-    int end_parity = 0;
-    bool synced = false;
-    size_t cell = 0;
-    cudaEvent_t done = nullptr;
-    // inputs of the build, kept for the transparent rebuild on capacity overflow
-    const uint8_t* src = nullptr;
-    size_t n = 0;
-    uint32_t carry_parity = 0;
-    uint64_t pos_bias = 0;
-    uint64_t out_base = 1;
-    const uint32_t* d_shard_par = nullptr;  // device-resident shard parities (multi-GPU), or null
-    uint32_t shard_rank = 0;
-    uint64_t* d_result2 = nullptr;          // optional caller-owned device copy of {count, parity}
-    // speculative sharded build: carry cell {0, carry parity, decisive quote found, redo flag} (device / pinned mirror)
-    bool speculative = false;
-    bool verified = false;
-    size_t carry_cell = 0;
-    uint8_t* d_bytes_owned = nullptr;
-    // Tape metadata (TapeCore::init)
-    bool tape_ready = false;
-    uint32_t field_cnt = 0, record_cnt = 0;
-    uint64_t jump = 0;
-    int crlf = 0;
-};
-
-namespace {
+namespace csvb200 {
 
 int fail(csvb200_ctx* ctx, int code, const std::string& msg)
 {
@@ -86,15 +24,13 @@ int fail(csvb200_ctx* ctx, int code, const std::string& msg)
     return code;
 }
 
-#define CU_TRY(ctx, expr)                                                                       \
-    do {                                                                                        \
-        cudaError_t e_ = (expr);                                                                \
-        if (e_ != cudaSuccess) {                                                                \
-            cudaGetLastError();                                                                 \
-            return fail((ctx), e_ == cudaErrorMemoryAllocation ? CSVB200_ERR_OOM : CSVB200_ERR_CUDA, \
-                        std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
-        }                                                                                       \
-    } while (0)
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes attr{};
+    const bool ok = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return ok;
+}
 
 int ensure_scratch(csvb200_ctx* ctx, size_t bytes)
 {
@@ -108,6 +44,10 @@ int ensure_scratch(csvb200_ctx* ctx, size_t bytes)
     ctx->scratch_bytes = nb;
     return CSVB200_OK;
 }
+
+}  // namespace csvb200
+
+namespace {
 
 size_t initial_cap(const csvb200_ctx* ctx, size_t n)
 {
@@ -259,16 +199,16 @@ int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint3
     return CSVB200_OK;
 }
 
+}  // namespace
+
+namespace csvb200 {
+
 // host -> device copy of n bytes; pinned sources go straight to cudaMemcpyAsync, pageable ones
 // through the context's pinned staging ring.
 int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n)
 {
     if (n == 0) return CSVB200_OK;
-    cudaPointerAttributes attr{};
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&attr, h_src) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (pinned) {
+    if (is_pinned(h_src)) {
         CU_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, ctx->stream));
         return CSVB200_OK;
     }
@@ -292,7 +232,7 @@ int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n)
     return CSVB200_OK;
 }
 
-}  // namespace
+}  // namespace csvb200
 
 extern "C" {
 
@@ -369,6 +309,7 @@ void csvb200_ctx_destroy(csvb200_ctx* ctx)
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_cells) cudaFree(ctx->d_cells);
     if (ctx->h_cells) cudaFreeHost(ctx->h_cells);
+    if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
     for (int b = 0; b < kStageBufs; ++b) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
         if (ctx->stage_free[b]) cudaEventDestroy(ctx->stage_free[b]);
@@ -885,14 +826,6 @@ static int seek_prepare(csvb200_index* idx)
     return CSVB200_OK;
 }
 
-static bool is_pinned(const void* p)
-{
-    cudaPointerAttributes attr{};
-    const bool ok = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    return ok;
-}
-
 // Host arrays in / out.  Queries go up and ranges come down in chunks of kSeekChunk queries on two
 // streams (H2D + kernel on the context's stream, D2H on the copy stream), double buffered, so a large
 // batch costs about max(up, down) of PCIe time instead of their sum plus the kernel.  Pinned caller
@@ -925,7 +858,6 @@ static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fl
         if (d_fld) cudaFreeAsync(d_fld, s_up);
         if (d_out) cudaFreeAsync(d_out, s_up);
         if (d_oob) cudaFreeAsync(d_oob, s_up);
-        if (h_stage) cudaFreeHost(h_stage);
         for (int i = 0; i < 2; ++i) {
             if (k_done[i]) cudaEventDestroy(k_done[i]);
             if (d_done[i]) cudaEventDestroy(d_done[i]);
@@ -947,7 +879,16 @@ static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fl
     SEEK_TRY(cudaMallocAsync((void**)&d_out, nslots * chunk * sizeof(csvb200_range), s_up));
     SEEK_TRY(cudaMallocAsync((void**)&d_oob, sizeof(uint32_t), s_up));
     SEEK_TRY(cudaMemsetAsync(d_oob, 0, sizeof(uint32_t), s_up));
-    if (!direct) SEEK_TRY(cudaHostAlloc((void**)&h_stage, nslots * slot_bytes, cudaHostAllocDefault));
+    if (!direct) {
+        if (ctx->seek_stage_bytes < nslots * slot_bytes) {   // page-locking is slow: keep the buffer in the context
+            if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
+            ctx->h_seek_stage = nullptr;
+            ctx->seek_stage_bytes = 0;
+            SEEK_TRY(cudaHostAlloc((void**)&ctx->h_seek_stage, nslots * slot_bytes, cudaHostAllocDefault));
+            ctx->seek_stage_bytes = nslots * slot_bytes;
+        }
+        h_stage = ctx->h_seek_stage;
+    }
     for (int i = 0; i < nslots; ++i) {
         SEEK_TRY(cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
         SEEK_TRY(cudaEventCreateWithFlags(&d_done[i], cudaEventDisableTiming));

@@ -1,0 +1,93 @@
+// ctx.h -- private definitions shared by the host-side translation units of libcsvb200
+// (api.cu: the C ABI; stream.cu: streaming ingest).  Not part of the public interface.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/csvb200.h"
+#include "internal.h"
+
+namespace csvb200 {
+constexpr size_t kCells = 4096;              // result cells (4 x u64 each): a ring of kRingCells + one scratch cell
+constexpr size_t kCellWords = 4;
+constexpr size_t kRingCells = kCells - 1;    // the last cell is the out-of-bounds flag of the async seek calls
+constexpr uint64_t kDefaultPredictWindow = 64u << 10;
+constexpr size_t kStageBytes = 32u << 20;    // pinned staging buffers for pageable input
+constexpr int kStageBufs = 2;
+constexpr size_t kE2eChunk = 64u << 20;      // H2D / kernel / D2H pipeline granularity
+}  // namespace csvb200
+
+struct csvb200_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of finished index segments (overlaps H2D)
+    cudaStream_t stream = nullptr;       // the stream work is issued on
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    bool timed = false;
+    uint8_t* d_scratch = nullptr;  // [16 B ticket cell][look-back descriptors]
+    size_t scratch_bytes = 0;
+    uint64_t* d_cells = nullptr;
+    uint64_t* h_cells = nullptr;
+    size_t next_cell = 0;
+    uint8_t* h_seek_stage = nullptr;   // pinned staging of the batched seeks from pageable arrays (kept across calls)
+    size_t seek_stage_bytes = 0;
+    uint8_t* h_stage[csvb200::kStageBufs] = {nullptr, nullptr};
+    cudaEvent_t stage_free[csvb200::kStageBufs] = {nullptr, nullptr};
+    uint32_t reserve_num = 1, reserve_den = 3;
+    uint64_t launches = 0;
+    int kernel_override = 0;  // 0 = auto, 1 = simple, 2 = tma (CSVB200_KERNEL)
+    uint32_t tune = 0;        // CSVB200_TUNE experiment knob
+    std::string err;
+};
+
+struct csvb200_index {
+    csvb200_ctx* ctx = nullptr;
+    uint64_t* d_index = nullptr;
+    size_t cap = 0;
+    size_t len = 0;
+    int end_parity = 0;
+    bool synced = false;
+    size_t cell = 0;
+    cudaEvent_t done = nullptr;
+    // inputs of the build, kept for the transparent rebuild on capacity overflow
+    const uint8_t* src = nullptr;
+    size_t n = 0;
+    uint32_t carry_parity = 0;
+    uint64_t pos_bias = 0;
+    uint64_t out_base = 1;
+    const uint32_t* d_shard_par = nullptr;  // device-resident shard parities (multi-GPU), or null
+    uint32_t shard_rank = 0;
+    uint64_t* d_result2 = nullptr;          // optional caller-owned device copy of {count, parity}
+    // speculative sharded build: carry cell {0, carry parity, decisive quote found, redo flag} (device / pinned mirror)
+    bool speculative = false;
+    bool verified = false;
+    size_t carry_cell = 0;
+    uint8_t* d_bytes_owned = nullptr;
+    // Tape metadata (TapeCore::init)
+    bool tape_ready = false;
+    uint32_t field_cnt = 0, record_cnt = 0;
+    uint64_t jump = 0;
+    int crlf = 0;
+};
+
+namespace csvb200 {
+
+int fail(csvb200_ctx* ctx, int code, const std::string& msg);
+int ensure_scratch(csvb200_ctx* ctx, size_t bytes);
+bool is_pinned(const void* p);
+// host -> device copy of n bytes on the context's stream; pinned sources go straight to cudaMemcpyAsync,
+// pageable ones through the context's pinned staging ring
+int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n);
+
+#define CU_TRY(ctx, expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            cudaGetLastError();                                                                 \
+            return csvb200::fail((ctx), e_ == cudaErrorMemoryAllocation ? CSVB200_ERR_OOM : CSVB200_ERR_CUDA, \
+                                 std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+        }                                                                                       \
+    } while (0)
+
+}  // namespace csvb200

@@ -44,7 +44,7 @@ __device__ __forceinline__ uint64_t virtual_prefix_desc(const BuildParams& p)
     uint64_t carry_count = p.carry_count;
     uint32_t carry_parity = p.carry_parity;
     if (p.carry != nullptr) {
-        carry_count = p.carry[0];
+        if (!p.carry_parity_only) carry_count = p.carry[0];
         carry_parity = (uint32_t)p.carry[1] & 1u;
     }
     if (p.shard_par != nullptr) {

@@ -36,6 +36,8 @@ struct BuildParams {
     uint64_t out_base;       // slot of the first entry produced by the virtual predecessor (1 after the sentinel)
     uint64_t pos_bias;       // added to every emitted byte position (global offset of the shard)
     const uint64_t* carry;   // optional device cell {entries so far, parity}; overrides the two below
+    uint32_t carry_parity_only;  // with `carry`: take only the parity from the cell, count = carry_count (streaming ingest:
+                                 // every chunk writes its own segment buffer from slot 0)
     uint64_t carry_count;    // entries emitted by earlier launches of the same build
     uint32_t carry_parity;   // quote parity entering byte 0 of `in`
     uint32_t num_tiles;

@@ -1,0 +1,400 @@
+// stream.cu -- streaming ingest (reference README.md:23 "Decisions" 3 wants streaming,
+// src/lib.rs:64-65 mmaps the whole file): csv of ANY size -> index, in bounded device and pinned memory.
+//
+//   reader (callback, or a pool of threads pread()ing a file)  ->  pinned input ring
+//   -> cudaMemcpyAsync H2D -> fused index kernel, chained to the previous chunk through a device cell that
+//      carries the quote parity (no host round trip between launches)
+//   -> D2H of the chunk's index segment on a second stream -> sink callback (or the caller's array)
+//
+// Chunk c+1 is read and uploaded while chunk c is indexed and chunk c-1 comes down; a chunk's segment
+// buffer on the device holds the worst case (one entry per byte), so no launch can overflow, and the
+// pinned output ring is drained in pieces when a chunk is denser than the ring slot.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "ctx.h"
+
+using namespace csvb200;
+
+namespace {
+
+constexpr int kSlots = 3;                        // ring depth: read / index / drain
+constexpr size_t kDefaultChunk = 16u << 20;
+constexpr size_t kMinChunk = 64u << 10;
+
+// A few persistent worker threads that split one job (a pread of a file range, or a memcpy) into
+// slices: a single thread moves ~10 GB/s, PCIe 5 x16 wants ~55.
+class SlicePool {
+public:
+    explicit SlicePool(int threads) : n_(std::max(1, threads))
+    {
+        for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~SlicePool()
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // runs fn(slice_index, slice_count) on every thread (the caller is slice 0) and waits
+    void run(const std::function<void(int, int)>& fn)
+    {
+        if (n_ == 1) {
+            fn(0, 1);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            pending_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        fn(0, n_);
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void loop(int id)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)>* fn = nullptr;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            if (fn) (*fn)(id, n_);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)>* fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+void parallel_memcpy(SlicePool& pool, void* dst, const void* src, size_t bytes)
+{
+    if (bytes < (4u << 20)) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    pool.run([&](int i, int n) {
+        const size_t per = ((bytes + n - 1) / n + 63) & ~size_t(63);
+        const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
+        if (b > a) std::memcpy(static_cast<uint8_t*>(dst) + a, static_cast<const uint8_t*>(src) + a, b - a);
+    });
+}
+
+struct Slot {
+    uint8_t* h_in = nullptr;       // pinned
+    uint64_t* h_out = nullptr;     // pinned, out_cap entries
+    uint8_t* d_in = nullptr;
+    uint64_t* d_seg = nullptr;     // chunk + 2 entries: the worst case (one entry per byte) + sentinel
+    cudaEvent_t k_done = nullptr;  // kernel + count read-back of the chunk in this slot
+    cudaEvent_t d_done = nullptr;  // last D2H out of d_seg
+    size_t bytes = 0;              // bytes of the chunk in flight
+    uint64_t offset = 0;           // global byte offset of the chunk
+    size_t cell = 0;
+    bool busy = false;
+};
+
+struct Pipeline {
+    csvb200_ctx* ctx = nullptr;
+    size_t chunk = 0, out_cap = 0;
+    Slot slot[kSlots];
+    size_t cells0 = 0;             // kSlots + 1 consecutive result cells; cell of chunk c = cells0 + c % (kSlots + 1)
+    uint64_t next_slot_global = 0; // global index slot of the next entry to hand to the sink
+    uint64_t total_bytes = 0;
+    uint32_t chunks = 0;
+    int end_parity = 0;
+
+    ~Pipeline()
+    {
+        if (!ctx) return;
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (Slot& s : slot) {
+            if (s.h_in) cudaFreeHost(s.h_in);
+            if (s.h_out) cudaFreeHost(s.h_out);
+            if (s.d_in) cudaFreeAsync(s.d_in, ctx->stream);
+            if (s.d_seg) cudaFreeAsync(s.d_seg, ctx->stream);
+            if (s.k_done) cudaEventDestroy(s.k_done);
+            if (s.d_done) cudaEventDestroy(s.d_done);
+        }
+        cudaGetLastError();
+    }
+
+    int init(csvb200_ctx* c, size_t chunk_bytes)
+    {
+        ctx = c;
+        chunk = std::max(kMinChunk, chunk_bytes ? chunk_bytes : kDefaultChunk);
+        chunk = (chunk + 127) & ~size_t(127);          // chunk boundaries stay 128-byte aligned (TMA rows)
+        out_cap = chunk / 2 + 4096;                    // entries per pinned output slot (4 x the chunk's bytes)
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+        cells0 = ctx->next_cell + kSlots + 1 <= kRingCells ? ctx->next_cell : 0;
+        ctx->next_cell = (cells0 + kSlots + 1) % kRingCells;
+        for (Slot& s : slot) {
+            CU_TRY(ctx, cudaHostAlloc((void**)&s.h_in, chunk, cudaHostAllocDefault));
+            CU_TRY(ctx, cudaHostAlloc((void**)&s.h_out, out_cap * sizeof(uint64_t), cudaHostAllocDefault));
+            CU_TRY(ctx, cudaMallocAsync((void**)&s.d_in, chunk + 16, ctx->stream));
+            CU_TRY(ctx, cudaMallocAsync((void**)&s.d_seg, (chunk + 2) * sizeof(uint64_t), ctx->stream));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&s.d_done, cudaEventDisableTiming));
+        }
+        // carry into chunk 0: {0, parity 0}
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_cells + (cells0 + kSlots) * kCellWords, 0, kCellWords * sizeof(uint64_t), ctx->stream));
+        return CSVB200_OK;
+    }
+
+    size_t cell_of(uint32_t c) const { return cells0 + c % (kSlots + 1); }
+
+    // enqueue H2D + kernel + count read-back of the chunk sitting in slot s (s.bytes > 0)
+    int launch(Slot& s)
+    {
+        const uint32_t c = chunks;
+        s.offset = total_bytes;
+        s.cell = cell_of(c);
+        const size_t prev_cell = c == 0 ? cells0 + kSlots : cell_of(c - 1);
+        cudaStream_t st = ctx->stream;
+        CU_TRY(ctx, cudaStreamWaitEvent(st, s.d_done, 0));   // the previous segment in this slot has left d_seg
+        CU_TRY(ctx, cudaMemcpyAsync(s.d_in, s.h_in, s.bytes, cudaMemcpyHostToDevice, st));
+        const bool use_tma = tma_path_usable(s.bytes) && ctx->kernel_override != 1;
+        const uint64_t num_tiles = (s.bytes + kTileBytes - 1) / kTileBytes;
+        const size_t sbytes = 128 + num_tiles * kDescStride * sizeof(uint64_t);
+        int rc = ensure_scratch(ctx, sbytes);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, st));
+        if (c == 0) CU_TRY(ctx, cudaMemsetAsync(s.d_seg, 0, sizeof(uint64_t), st));   // sentinel (src/reader.rs:216)
+        BuildParams p{};
+        p.in = s.d_in;
+        p.n = s.bytes;
+        p.index = s.d_seg;
+        p.cap = chunk + 2;
+        p.out_base = c == 0 ? 1 : 0;
+        p.pos_bias = s.offset;
+        p.carry = ctx->d_cells + prev_cell * kCellWords;
+        p.carry_parity_only = 1;
+        p.num_tiles = (uint32_t)num_tiles;
+        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
+        p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
+        p.result = ctx->d_cells + s.cell * kCellWords;
+        p.result2_words = 2;
+        p.tune = ctx->tune;
+        CU_TRY(ctx, use_tma ? launch_index_build_tma(p, st) : launch_index_build(p, st));
+        ctx->launches += 1;
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_cells + s.cell * kCellWords, ctx->d_cells + s.cell * kCellWords,
+                                    2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaEventRecord(s.k_done, st));
+        s.busy = true;
+        total_bytes += s.bytes;
+        ++chunks;
+        return CSVB200_OK;
+    }
+
+    // wait for the chunk in slot s, bring its segment down (in pieces of the pinned slot) and hand it on.
+    // direct_dst != nullptr: the caller's array is pinned, entries go straight into it.
+    int drain(Slot& s, const std::function<int(const uint64_t*, size_t, uint64_t)>& sink, uint64_t* direct_dst,
+              size_t direct_cap, bool* dst_small)
+    {
+        if (!s.busy) return CSVB200_OK;
+        CU_TRY(ctx, cudaEventSynchronize(s.k_done));
+        const uint64_t* h_cell = ctx->h_cells + s.cell * kCellWords;
+        const size_t count = (size_t)h_cell[0] + (s.offset == 0 ? 1 : 0);   // + sentinel in the first chunk
+        end_parity = (int)(h_cell[1] & 1u);
+        cudaStream_t sd = ctx->copy_stream;
+        CU_TRY(ctx, cudaStreamWaitEvent(sd, s.k_done, 0));
+        if (direct_dst) {
+            if (next_slot_global + count > direct_cap) {
+                *dst_small = true;
+            } else if (count) {
+                CU_TRY(ctx, cudaMemcpyAsync(direct_dst + next_slot_global, s.d_seg, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, sd));
+            }
+            CU_TRY(ctx, cudaEventRecord(s.d_done, sd));
+            next_slot_global += count;
+        } else {
+            for (size_t off = 0; off < count; off += out_cap) {
+                const size_t len = std::min(out_cap, count - off);
+                CU_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_seg + off, len * sizeof(uint64_t), cudaMemcpyDeviceToHost, sd));
+                CU_TRY(ctx, cudaStreamSynchronize(sd));
+                if (sink(s.h_out, len, next_slot_global) != 0) return fail(ctx, CSVB200_ERR_IO, "index sink reported an error");
+                next_slot_global += len;
+            }
+            CU_TRY(ctx, cudaEventRecord(s.d_done, sd));
+        }
+        s.busy = false;
+        return CSVB200_OK;
+    }
+};
+
+using ReadFn = std::function<long long(uint8_t*, size_t)>;   // fills up to cap bytes, < cap only at the end, < 0 = error
+using SinkFn = std::function<int(const uint64_t*, size_t, uint64_t)>;
+
+int run_pipeline(csvb200_ctx* ctx, size_t chunk_bytes, const ReadFn& read, const SinkFn& sink, uint64_t* direct_dst,
+                 size_t direct_cap, csvb200_stream_stats* stats)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    Pipeline pl;
+    int rc = pl.init(ctx, chunk_bytes);
+    if (rc) return rc;
+    bool dst_small = false, eof = false;
+    uint32_t head = 0, tail = 0;   // chunks launched / drained
+    while (!eof || tail < head) {
+        if (!eof && head - tail < (uint32_t)kSlots) {
+            Slot& s = pl.slot[head % kSlots];
+            // the host reads chunk `head` while the GPU works on the chunks before it
+            const long long got = read(s.h_in, pl.chunk);
+            if (got < 0) return fail(ctx, CSVB200_ERR_IO, "input reader reported an error");
+            if ((size_t)got < pl.chunk) eof = true;
+            if (got > 0 || head == 0) {
+                s.bytes = (size_t)got;
+                if (s.bytes == 0) {
+                    // empty input: the index is the sentinel alone
+                    const uint64_t zero = 0;
+                    if (direct_dst) {
+                        if (direct_cap < 1) dst_small = true;
+                        else direct_dst[0] = 0;
+                        pl.next_slot_global = 1;
+                    } else {
+                        if (sink(&zero, 1, 0) != 0) return fail(ctx, CSVB200_ERR_IO, "index sink reported an error");
+                        pl.next_slot_global = 1;
+                    }
+                    break;
+                }
+                rc = pl.launch(s);
+                if (rc) return rc;
+                ++head;
+            }
+            if (head - tail < (uint32_t)kSlots && !eof) continue;   // keep the ring full before blocking on a drain
+        }
+        if (tail < head) {
+            rc = pl.drain(pl.slot[tail % kSlots], sink, direct_dst, direct_cap, &dst_small);
+            if (rc) return rc;
+            ++tail;
+        }
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        stats->bytes = pl.total_bytes;
+        stats->entries = pl.next_slot_global;
+        stats->end_parity = pl.end_parity;
+        stats->chunks = pl.chunks;
+        stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (dst_small) return fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    return CSVB200_OK;
+}
+
+int default_threads()
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min(8u, std::max(1u, hw / 2));
+}
+
+}  // namespace
+
+extern "C" {
+
+int csvb200_index_build_stream(csvb200_ctx* ctx, csvb200_read_fn read_fn, void* read_user, csvb200_sink_fn sink_fn,
+                               void* sink_user, size_t chunk_bytes, csvb200_stream_stats* stats)
+{
+    if (!ctx || !read_fn || !sink_fn) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    // the reader may return short counts before the end of the input: keep asking until the chunk is full
+    ReadFn read = [&](uint8_t* dst, size_t cap) -> long long {
+        size_t got = 0;
+        while (got < cap) {
+            const size_t k = read_fn(read_user, dst + got, cap - got);
+            if (k == 0) break;
+            if (k > cap - got) return -1;
+            got += k;
+        }
+        return (long long)got;
+    };
+    SinkFn sink = [&](const uint64_t* e, size_t n, uint64_t first) { return sink_fn(sink_user, e, n, first); };
+    return run_pipeline(ctx, chunk_bytes, read, sink, nullptr, 0, stats);
+}
+
+int csvb200_index_build_file(csvb200_ctx* ctx, const char* path, uint64_t* dst, size_t dst_cap, size_t* len_out,
+                             csvb200_stream_stats* stats)
+{
+    if (!ctx || !path || !len_out || (!dst && dst_cap)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return fail(ctx, CSVB200_ERR_IO, std::string("open ") + path + ": " + std::strerror(errno));   // StructureError::Io
+    SlicePool pool(default_threads());
+    uint64_t file_off = 0;
+    bool io_error = false;
+    ReadFn read = [&](uint8_t* buf, size_t cap) -> long long {
+        // every pool thread preads its own slice of the chunk straight into the pinned buffer
+        std::atomic<size_t> total{0};
+        pool.run([&](int i, int n) {
+            const size_t per = ((cap + n - 1) / n + 4095) & ~size_t(4095);
+            size_t a = std::min(cap, per * i);
+            const size_t b = std::min(cap, per * (i + 1));
+            while (a < b) {
+                const ssize_t k = ::pread(fd, buf + a, b - a, (off_t)(file_off + a));
+                if (k < 0) {
+                    io_error = true;
+                    return;
+                }
+                if (k == 0) break;   // end of file inside (or before) this slice
+                a += (size_t)k;
+                total += (size_t)k;
+            }
+        });
+        if (io_error) return -1;
+        file_off += total.load();
+        return (long long)total.load();
+    };
+    csvb200_stream_stats local{};
+    csvb200_stream_stats* st = stats ? stats : &local;
+    int rc;
+    if (dst && is_pinned(dst)) {
+        SinkFn none = [](const uint64_t*, size_t, uint64_t) { return 0; };
+        rc = run_pipeline(ctx, 0, read, none, dst, dst_cap, st);
+    } else {
+        bool small = false;
+        SinkFn sink = [&](const uint64_t* e, size_t n, uint64_t first) {
+            if (first + n > dst_cap) {
+                small = true;        // keep counting so *len_out tells the caller what to allocate
+                return 0;
+            }
+            parallel_memcpy(pool, dst + first, e, n * sizeof(uint64_t));
+            return 0;
+        };
+        rc = run_pipeline(ctx, 0, read, sink, nullptr, 0, st);
+        if (!rc && small) rc = fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    }
+    ::close(fd);
+    *len_out = (size_t)st->entries;
+    return rc;
+}
+
+}  // extern "C"

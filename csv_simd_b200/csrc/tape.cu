@@ -22,37 +22,59 @@ __device__ __forceinline__ uint64_t ldg_u64(const uint64_t* p)
     return v;
 }
 
+__device__ __forceinline__ bool slot_ok(const TapeValidateParams& p, uint64_t s, uint64_t k, uint64_t pos, uint32_t b,
+                                        bool in_range)
+{
+    if (!in_range) return false;
+    const uint64_t jump = p.jump;
+    if (p.crlf) {
+        if (k + 2 < jump) return b == 0x2Cu;
+        if (k + 2 == jump) return b == 0x0Du;
+        return b == 0x0Au && ldg_u64(p.index + s - 1) + 1 == pos;
+    }
+    return k + 1 < jump ? b == 0x2Cu : (b == 0x0Au || b == 0x0Du);
+}
+
 __global__ void __launch_bounds__(256) tape_validate_kernel(const TapeValidateParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t jump = p.jump;
-    const uint32_t step = (uint32_t)(32ull % jump);   // k advances by 32 slots per warp iteration
+    const uint64_t last = p.index_len - 1;            // slots are 1 .. last; i = s - 1 in [0, last)
+    const uint32_t step = (uint32_t)(32ull % jump);   // k advances by 32 slots per warp row
     uint64_t bad = UINT64_MAX;
-    // each warp owns runs of kRun consecutive slots, 32 at a time: one modulo per run, then k += 32 (mod jump)
+    // each warp owns runs of kRun consecutive slots: one modulo per run, then k += 32 (mod jump) per row.
+    // kUnroll rows are in flight together: the byte load depends on the index load, so the loop is
+    // latency-bound without them (0.62 -> measured again in profiles/).
+    constexpr int kUnroll = 4;
     constexpr uint64_t kRun = 32 * 64;
-    for (uint64_t run = warp0 * kRun; run < p.index_len - 1; run += warps * kRun) {
-        const uint64_t run_end = run + kRun < p.index_len - 1 ? run + kRun : p.index_len - 1;
-        uint64_t k = (run + lane) % jump;            // slot s = 1 + run + lane  ->  k = (s - 1) % jump
-        for (uint64_t i = run + lane; i < run_end; i += 32) {
-            const uint64_t s = i + 1;
-            const uint64_t pos = ldg_u64(p.index + s);
-            const uint64_t rel = pos - p.pos_bias;
-            bool ok = rel < p.n;
-            if (ok) {
-                const uint32_t b = p.bytes[rel];
-                if (p.crlf) {
-                    if (k + 2 < jump) ok = b == 0x2Cu;
-                    else if (k + 2 == jump) ok = b == 0x0Du;
-                    else ok = b == 0x0Au && ldg_u64(p.index + s - 1) + 1 == pos;
-                } else {
-                    ok = k + 1 < jump ? b == 0x2Cu : (b == 0x0Au || b == 0x0Du);
-                }
+    for (uint64_t run = warp0 * kRun; run < last; run += warps * kRun) {
+        const uint64_t run_end = run + kRun < last ? run + kRun : last;
+        uint64_t k = (run + lane) % jump;             // slot s = 1 + run + lane  ->  k = (s - 1) % jump
+        for (uint64_t i = run + lane; i < run_end; i += 32 * kUnroll) {
+            uint64_t pos[kUnroll], kk[kUnroll];
+            uint32_t byte[kUnroll];
+            bool live[kUnroll], inr[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                live[u] = i + 32ull * u < run_end;
+                pos[u] = live[u] ? ldg_u64(p.index + i + 32ull * u + 1) : 0ull;
+                kk[u] = k;
+                k += step;
+                if (k >= jump) k -= jump;
             }
-            if (!ok && s < bad) bad = s;
-            k += step;
-            if (k >= jump) k -= jump;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint64_t rel = pos[u] - p.pos_bias;
+                inr[u] = rel < p.n;
+                byte[u] = live[u] && inr[u] ? p.bytes[rel] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint64_t s = i + 32ull * u + 1;
+                if (live[u] && !slot_ok(p, s, kk[u], pos[u], byte[u], inr[u]) && s < bad) bad = s;
+            }
         }
     }
     // warp minimum, one atomic per warp that saw a violation

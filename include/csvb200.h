@@ -100,6 +100,34 @@ int csvb200_index_build_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n
 int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst,
                                 size_t dst_cap, size_t* len_out);
 
+/* ---- streaming ingest (reference README.md:23 "Decisions" 3; src/lib.rs:64-65 maps the whole file) -- */
+/* csv of any size -> index in bounded device and pinned memory: the input is pulled in chunks into a
+ * pinned ring, uploaded, indexed by launches chained through a device-resident quote-parity cell, and
+ * every finished index segment is handed to the sink in order while later chunks are still going up.
+ *   read : fill dst (pinned) with up to cap of the NEXT input bytes, return the count; 0 = end of input
+ *   sink : consume `count` consecutive index entries starting at global slot first_slot (entries are
+ *          global byte offsets; the sentinel index[0] = 0 arrives first); the pointer is only valid
+ *          during the call; a non-zero return aborts the build with CSVB200_ERR_IO
+ * chunk_bytes = 0 selects the default (16 MiB). */
+typedef size_t (*csvb200_read_fn)(void* user, uint8_t* dst, size_t cap);
+typedef int (*csvb200_sink_fn)(void* user, const uint64_t* entries, size_t count, uint64_t first_slot);
+typedef struct csvb200_stream_stats {
+    uint64_t bytes;    /* input bytes consumed */
+    uint64_t entries;  /* index entries produced, sentinel included */
+    double seconds;    /* wall time of the call */
+    uint32_t chunks;
+    int end_parity;    /* quote parity after the last byte */
+} csvb200_stream_stats;
+int csvb200_index_build_stream(csvb200_ctx* ctx, csvb200_read_fn read, void* read_user, csvb200_sink_fn sink,
+                               void* sink_user, size_t chunk_bytes, csvb200_stream_stats* stats);
+/* csv_simd::create's data path for a file (src/lib.rs:61-74: File::open -> Mmap::map -> reader::read):
+ * a pool of threads pread()s the file straight into the pinned ring; the index lands in dst (DMA'd in
+ * place when dst is pinned, else copied out of the pinned ring by the same pool).  *len_out receives
+ * the entry count even when dst_cap is too small (CSVB200_ERR_CAPACITY); a file that cannot be opened
+ * or read is CSVB200_ERR_IO (StructureError::Io). */
+int csvb200_index_build_file(csvb200_ctx* ctx, const char* path, uint64_t* dst, size_t dst_cap, size_t* len_out,
+                             csvb200_stream_stats* stats);
+
 /* ---- sharded build (multi-GPU, SURVEY 8e / README.md:24 "splitting work without first knowing
  * record breaks") --------------------------------------------------------------------------- */
 /* Pass A: quote parity (0/1) of a device-resident shard -- the only thing that must cross GPUs

@@ -575,4 +575,24 @@ size_t oracle_field_value(const uint8_t *raw, size_t len, uint32_t flags, uint8_
     return b - a;
 }
 
+/* whole column through the seek_field restatement + oracle_field_value; offsets[nrec + 1]; out may be
+ * NULL (sizing pass).  Returns the total length. */
+uint64_t oracle_materialize_column(const uint8_t *bytes, size_t n, const uint64_t *index, size_t index_len,
+                                   uint32_t record_cnt, uint32_t field_cnt, int crlf, uint32_t field_idx,
+                                   uint32_t first_record, uint32_t nrec, uint32_t flags,
+                                   uint64_t *offsets, uint8_t *out)
+{
+    uint64_t acc = 0;
+    for (uint32_t i = 0; i < nrec; ++i) {
+        uint64_t a = 0, b = 0;
+        int found = 0;
+        offsets[i] = acc;
+        if (oracle_seek_field(index, index_len, n, record_cnt, field_cnt, crlf, first_record + i, field_idx,
+                              &a, &b, &found) == 0 && found && a <= b && b <= n)
+            acc += oracle_field_value(bytes + a, (size_t)(b - a), flags, out ? out + acc : NULL);
+    }
+    offsets[nrec] = acc;
+    return acc;
+}
+
 uint64_t oracle_blsr(uint64_t x) { return x & (x ? x - 1 : 0); }

@@ -67,6 +67,10 @@ int oracle_chunks(uint32_t record_cnt, uint64_t jump, uint8_t num, oracle_chunk 
 uint64_t oracle_tape_first_bad_slot(const uint8_t *bytes, size_t n, const uint64_t *index,
                                     size_t index_len, uint32_t field_cnt, int crlf);
 size_t oracle_field_value(const uint8_t *raw, size_t len, uint32_t flags, uint8_t *out);
+uint64_t oracle_materialize_column(const uint8_t *bytes, size_t n, const uint64_t *index, size_t index_len,
+                                   uint32_t record_cnt, uint32_t field_cnt, int crlf, uint32_t field_idx,
+                                   uint32_t first_record, uint32_t nrec, uint32_t flags,
+                                   uint64_t *offsets, uint8_t *out);
 uint64_t oracle_blsr(uint64_t x);
 
 #ifdef __cplusplus

@@ -92,6 +92,10 @@ def lib():
         L.oracle_tape_first_bad_slot.restype = C.c_uint64
         L.oracle_field_value.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.oracle_field_value.restype = C.c_size_t
+        L.oracle_materialize_column.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
+                                                C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                C.c_void_p]
+        L.oracle_materialize_column.restype = C.c_uint64
         L.oracle_blsr.argtypes = [C.c_uint64]
         L.oracle_blsr.restype = C.c_uint64
         _lib = L
@@ -265,15 +269,15 @@ def materialize_column(data, index: np.ndarray, record_cnt: int, field_cnt: int,
                        first_record: int, nrec: int, flags: int):
     """(offsets[nrec+1], packed bytes): field `field_idx` of records first_record .. +nrec through the
     seek_field restatement (a record that seek_field reports as None contributes an empty value)."""
-    raw = data if isinstance(data, (bytes, bytearray)) else np.asarray(data, dtype=np.uint8).tobytes()
-    offs, parts, acc = [0], [], 0
-    for r in range(first_record, first_record + nrec):
-        rg = seek_field(index, len(raw), record_cnt, field_cnt, crlf, r, field_idx)
-        v = field_value(raw[rg[0]:rg[1]], flags) if rg is not None and rg[1] >= rg[0] else b""
-        parts.append(v)
-        acc += len(v)
-        offs.append(acc)
-    return np.array(offs, dtype=np.uint64), b"".join(parts)
+    a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, dtype=np.uint8)
+    index = np.ascontiguousarray(index, dtype=np.uint64)
+    offs = np.zeros(nrec + 1, dtype=np.uint64)
+    args = (a.ctypes.data, a.size, index.ctypes.data, index.size, record_cnt, field_cnt, int(crlf), field_idx,
+            first_record, nrec, flags, offs.ctypes.data)
+    total = lib().oracle_materialize_column(*args, None)
+    out = np.zeros(max(int(total), 1), dtype=np.uint8)
+    lib().oracle_materialize_column(*args, out.ctypes.data)
+    return offs, out[:int(total)].tobytes()
 
 
 def blsr(x: int) -> int:

@@ -610,3 +610,83 @@ def test_materialize_column_crlf_and_device_form(ctx):
         assert d_out.cpu().numpy()[:len(w_out)].tobytes() == w_out
     assert idx.materialize_column(2, 1, 1, 3)[1].tobytes() == b"INTERNAL MED, CARD. ELECTROPHYSIOLOGY"
     idx.free()
+
+
+# ---- streaming ingest ---------------------------------------------------------
+def test_stream_build_vs_oracle(ctx):
+    """csvb200_index_build_stream: many small chunks (quote regions, CRLF pairs and "" escapes cut by the
+    chunk boundaries), short reads from the reader, segments delivered in order."""
+    q, _ = gen.quoted(3 << 20, seed=47)
+    raw = q.tobytes()
+    want = O.read_sse(raw)
+    for chunk, read_max in ((64 << 10, 1 << 30), (64 << 10, 5000), (1 << 20, 777777), (0, 1 << 30)):
+        pos = [0]
+        parts, firsts = [], []
+
+        def read(cap):
+            k = min(cap, read_max, len(raw) - pos[0])
+            b = raw[pos[0]:pos[0] + k]
+            pos[0] += k
+            return b
+
+        def sink(entries, first):
+            parts.append(entries.copy())
+            firsts.append(first)
+
+        st = ctx.index_build_stream(read, sink, chunk)
+        got = np.concatenate(parts)
+        assert got.shape == want.shape and (got == want).all(), (chunk, read_max)
+        assert firsts == list(np.cumsum([0] + [p.size for p in parts[:-1]]))
+        assert st["bytes"] == len(raw) and st["entries"] == want.size and st["end_parity"] == (raw.count(b'"') & 1)
+        assert st["chunks"] == -(-len(raw) // (chunk or (16 << 20)))
+    # empty input: the sentinel alone
+    parts = []
+    st = ctx.index_build_stream(lambda cap: b"", lambda e, f: parts.append(e.copy()), 0)
+    assert st["entries"] == 1 and len(parts) == 1 and parts[0].tolist() == [0]
+    # a failing sink aborts with Io
+    with pytest.raises(ZeroDivisionError):
+        pos = [0]
+        ctx.index_build_stream(lambda cap: raw[:1000] if not pos[0] and not pos.__setitem__(0, 1) else b"", lambda e, f: 1 / 0, 0)
+    # dense chunk: more entries than a pinned output slot holds (drained in pieces)
+    dense = b"," * (300 << 10)
+    parts = []
+    pos = [0]
+
+    def read2(cap):
+        k = min(cap, len(dense) - pos[0])
+        pos[0] += k
+        return dense[:k]
+
+    ctx.index_build_stream(read2, lambda e, f: parts.append(e.copy()), 128 << 10)
+    got = np.concatenate(parts)
+    assert got.size == len(dense) + 1 and (got[1:] == np.arange(len(dense), dtype=np.uint64)).all()
+
+
+def test_index_build_file_vs_oracle(ctx):
+    import torch
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "big.csv")
+        q, _ = gen.quoted(40 << 20, seed=48)     # 3 chunks of 16 MiB
+        q.tofile(path)
+        want = O.read_sse(q)
+        got, st = ctx.index_build_file(path)      # pageable destination: copied out of the pinned ring
+        assert got.shape == want.shape and (got == want).all()
+        assert st["bytes"] == q.size and st["chunks"] == 3
+        h = torch.zeros(want.size + 8, dtype=torch.int64).pin_memory()   # pinned destination: DMA in place
+        ln, st = ctx.index_build_file_ptr(path, h.data_ptr(), h.numel())
+        assert ln == want.size and (h.numpy()[:ln].view(np.uint64) == want).all()
+        with pytest.raises(BufferError):
+            ctx.index_build_file_ptr(path, h.data_ptr(), 100)
+        small = np.empty(10, dtype=np.uint64)
+        got, _ = ctx.index_build_file(path, small)           # too small: retried with the reported size
+        assert (got == want).all()
+        for name in ("sample.csv", "sample_rx.csv", "reader_test01.csv"):
+            p2 = os.path.join(d, name)
+            open(p2, "wb").write(golden_bytes(name))
+            got, _ = ctx.index_build_file(p2)
+            assert (got == O.read_sse(golden_bytes(name))).all()
+        open(os.path.join(d, "empty.csv"), "wb").close()
+        got, _ = ctx.index_build_file(os.path.join(d, "empty.csv"))
+        assert got.tolist() == [0]
+    with pytest.raises(cs.Io):
+        ctx.index_build_file("/nonexistent/definitely_missing.csv")
