@@ -94,6 +94,10 @@ SIGNATURES = {
                                              C.c_void_p, C.c_size_t, szp]),
     "csvb200_materialize_column_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                     C.c_void_p, C.c_void_p, C.c_size_t]),
+    "csvb200_validate_utf8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, C.POINTER(C.c_int)]),
+    "csvb200_validate_utf8_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "csvb200_index_load": (C.c_int, [C.c_void_p, C.c_char_p, vpp]),
     "csvb200_block_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "csvb200_class_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

@@ -200,6 +200,25 @@ class Context:
             C.c_void_p(d_result_out), C.byref(h)))
         return StructureIndex(self, h)
 
+    # -- input validation / on-disk index ------------------------------------------------------
+    def validate_utf8(self, data):
+        """(valid_up_to or None when well-formed UTF-8, is_ascii) -- csvb200_validate_utf8."""
+        a = _as_u8(data)
+        v, asc = C.c_uint64(), C.c_int()
+        self._check(self._lib.csvb200_validate_utf8(self._h, a.ctypes.data, a.size, C.byref(v), C.byref(asc)))
+        if a.size == 0:
+            return None, True
+        return (None if v.value == 0xFFFFFFFFFFFFFFFF else v.value), bool(asc.value)
+
+    def validate_utf8_device(self, dev_ptr: int, n: int, d_result: int):
+        self._check(self._lib.csvb200_validate_utf8_device(self._h, C.c_void_p(dev_ptr), n, C.c_void_p(d_result)))
+
+    def index_load(self, path: str) -> "StructureIndex":
+        import os
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_load(self._h, os.fsencode(path), C.byref(h)))
+        return StructureIndex(self, h)
+
     # -- K1 known-answer exports ------------------------------------------------------------
     def block_masks(self, data):
         a = _as_u8(data)
@@ -275,6 +294,10 @@ class StructureIndex:
         r, c = C.c_int(), C.c_int()
         self.ctx._check(self._lib.csvb200_index_shard_redone(self._h, C.byref(r), C.byref(c)))
         return bool(r.value), c.value
+
+    def save(self, path: str):
+        import os
+        self.ctx._check(self._lib.csvb200_index_save(self._h, os.fsencode(path)))
 
     def copy_out_ptr(self, dst_ptr: int, dst_cap: int):
         self.ctx._check(self._lib.csvb200_index_copy_out(self._h, C.c_void_p(dst_ptr), dst_cap))

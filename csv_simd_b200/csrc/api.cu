@@ -1129,6 +1129,137 @@ int csvb200_materialize_column(csvb200_index* idx, uint32_t field_idx, uint32_t 
     return rc;
 }
 
+int csvb200_validate_utf8_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint64_t* d_result)
+{
+    if (!ctx || !d_result || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemsetAsync(d_result, 0xff, sizeof(uint64_t), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_result + 1, 0, sizeof(uint64_t), ctx->stream));
+    CU_TRY(ctx, launch_utf8_validate(static_cast<const uint8_t*>(dev_bytes), n, d_result, ctx->stream));
+    if (n) ctx->launches += 1;
+    return CSVB200_OK;
+}
+
+int csvb200_validate_utf8(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* valid_up_to, int* is_ascii)
+{
+    if (!ctx || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    uint8_t* d_in = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_in, n + 16, ctx->stream));
+    int rc = upload(ctx, d_in, host_bytes, n);
+    const size_t cell = ctx->next_cell;
+    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+    uint64_t* d_cell = ctx->d_cells + cell * kCellWords;
+    uint64_t* h_cell = ctx->h_cells + cell * kCellWords;
+    if (!rc) rc = csvb200_validate_utf8_device(ctx, d_in, n, d_cell);
+    if (!rc) {
+        CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (valid_up_to) *valid_up_to = h_cell[0];
+        if (is_ascii) *is_ascii = h_cell[1] ? 0 : 1;
+    }
+    cudaFreeAsync(d_in, ctx->stream);
+    return rc;
+}
+
+// ---- on-disk index: 64-byte little-endian header + the u64 entries ----------------
+namespace {
+struct IndexFileHeader {
+    char magic[8];          // "CSVB2IDX"
+    uint32_t version;       // 1
+    uint32_t flags;         // bit 0: Tape metadata present, bit 1: CRLF
+    uint64_t input_bytes;
+    uint64_t entries;
+    uint32_t field_cnt;
+    uint32_t record_cnt;
+    uint64_t jump;
+    uint64_t end_parity;
+    uint64_t checksum;      // wrapping sum of the entries
+};
+static_assert(sizeof(IndexFileHeader) == 64, "on-disk header is 64 bytes");
+const char kIndexMagic[8] = {'C', 'S', 'V', 'B', '2', 'I', 'D', 'X'};
+}  // namespace
+
+int csvb200_index_save(csvb200_index* idx, const char* path)
+{
+    if (!idx || !path) return CSVB200_ERR_INVALID_ARG;
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    std::vector<uint64_t> host(idx->len);
+    rc = csvb200_index_copy_out(idx, host.data(), host.size());
+    if (rc) return rc;
+    IndexFileHeader h{};
+    std::memcpy(h.magic, kIndexMagic, 8);
+    h.version = 1;
+    h.flags = (idx->tape_ready ? 1u : 0u) | (idx->crlf ? 2u : 0u);
+    h.input_bytes = idx->n;
+    h.entries = idx->len;
+    h.field_cnt = idx->field_cnt;
+    h.record_cnt = idx->record_cnt;
+    h.jump = idx->jump;
+    h.end_parity = (uint64_t)idx->end_parity;
+    for (uint64_t v : host) h.checksum += v;
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(ctx, CSVB200_ERR_IO, std::string("open ") + path + ": " + std::strerror(errno));
+    const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 &&
+                    (host.empty() || std::fwrite(host.data(), sizeof(uint64_t), host.size(), f) == host.size());
+    const bool closed = std::fclose(f) == 0;
+    if (!ok || !closed) return fail(ctx, CSVB200_ERR_IO, std::string("write ") + path + " failed");
+    return CSVB200_OK;
+}
+
+int csvb200_index_load(csvb200_ctx* ctx, const char* path, csvb200_index** out)
+{
+    if (!ctx || !path || !out) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(ctx, CSVB200_ERR_IO, std::string("open ") + path + ": " + std::strerror(errno));
+    IndexFileHeader h{};
+    std::vector<uint64_t> host;
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, kIndexMagic, 8) == 0 && h.version == 1;
+    if (ok) {
+        std::fseek(f, 0, SEEK_END);
+        const long long size = std::ftell(f);
+        ok = size >= 0 && (unsigned long long)size == sizeof(h) + h.entries * sizeof(uint64_t) && h.entries >= 1;
+        std::fseek(f, (long)sizeof(h), SEEK_SET);
+    }
+    if (ok) {
+        host.resize(h.entries);
+        ok = std::fread(host.data(), sizeof(uint64_t), host.size(), f) == host.size();
+    }
+    std::fclose(f);
+    uint64_t sum = 0;
+    for (uint64_t v : host) sum += v;
+    if (!ok || sum != h.checksum || host[0] != 0)
+        return fail(ctx, CSVB200_ERR_INVALID_CSV_FORMAT, std::string(path) + ": not a csvb200 index file (bad magic, size or checksum)");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    csvb200_index* idx = nullptr;
+    int rc = new_index(ctx, &idx);
+    if (rc) return rc;
+    idx->cap = host.size();
+    cudaError_t e = cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(idx->d_index, host.data(), host.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        csvb200_index_free(idx);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? CSVB200_ERR_OOM : CSVB200_ERR_CUDA, std::string("index load: ") + cudaGetErrorString(e));
+    }
+    idx->len = host.size();
+    idx->n = h.input_bytes;
+    idx->end_parity = (int)(h.end_parity & 1u);
+    idx->synced = true;
+    if (h.flags & 1u) {
+        idx->tape_ready = true;
+        idx->crlf = (h.flags & 2u) ? 1 : 0;
+        idx->field_cnt = h.field_cnt;
+        idx->record_cnt = h.record_cnt;
+        idx->jump = h.jump;
+    }
+    *out = idx;
+    return CSVB200_OK;
+}
+
 int csvb200_block_masks(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* quote_words,
                         uint64_t* sep_words)
 {

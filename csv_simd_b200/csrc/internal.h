@@ -118,6 +118,10 @@ cudaError_t launch_tape_validate(const TapeValidateParams& p, cudaStream_t strea
 cudaError_t launch_gather_slots(const uint64_t* index, uint64_t index_len, const uint64_t* slots, uint64_t n,
                                 uint64_t* out, cudaStream_t stream);
 
+// K7 ASCII / UTF-8 validation (validate.cu): result[0] (preset UINT64_MAX) <- start of the first ill-formed
+// sequence, result[1] (preset 0) <- 1 when any byte is >= 0x80
+cudaError_t launch_utf8_validate(const uint8_t* in, uint64_t n, uint64_t* result, cudaStream_t stream);
+
 // K6 column materialisation (materialize.cu)
 struct MaterializeParams {
     const uint64_t* index;

@@ -17,6 +17,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -313,10 +314,16 @@ int run_pipeline(csvb200_ctx* ctx, size_t chunk_bytes, const ReadFn& read, const
     return CSVB200_OK;
 }
 
+// CSVB200_IO_THREADS overrides; default: half the hardware threads, at most 16 (the other ranks of a
+// one-process-per-GPU job need cores too)
 int default_threads()
 {
+    if (const char* e = std::getenv("CSVB200_IO_THREADS")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 256) return v;
+    }
     const unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::min(8u, std::max(1u, hw / 2));
+    return (int)std::min(16u, std::max(1u, hw / 2));
 }
 
 }  // namespace

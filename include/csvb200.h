@@ -248,6 +248,22 @@ int csvb200_materialize_column(csvb200_index* idx, uint32_t field_idx, uint32_t 
 int csvb200_materialize_column_device(csvb200_index* idx, uint32_t field_idx, uint32_t first_record, uint32_t nrec,
                                       uint32_t flags, uint64_t* d_offsets, uint8_t* d_out, size_t out_cap);
 
+/* ---- input validation (the reference's is_ascii, src/reader.rs:26-132, and its dead UTF-8 checker,
+ * src/avx/utf8check.rs; seek_record builds &str unchecked, src/record_source.rs:97-101) ----------- */
+/* One pass over the bytes: *is_ascii = no byte >= 0x80 (is_ascii's answer); *valid_up_to = what
+ * core::str::from_utf8 reports, the start of the first ill-formed UTF-8 sequence, UINT64_MAX when the
+ * input is well-formed.  Device form: asynchronous, d_result = {valid_up_to, 1 if any byte >= 0x80}. */
+int csvb200_validate_utf8(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* valid_up_to, int* is_ascii);
+int csvb200_validate_utf8_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint64_t* d_result);
+
+/* ---- on-disk index: 64-byte little-endian header {"CSVB2IDX", version 1, flags, input bytes, entries,
+ * field_cnt, record_cnt, jump, end parity, wrapping sum of the entries} + the u64 entries ------------ */
+int csvb200_index_save(csvb200_index* idx, const char* path);
+/* The loaded index supports the Tape / seek calls (metadata restored when it was saved after
+ * csvb200_tape_init); calls that need the input bytes report CSVB200_ERR_INVALID_STATE.  A file with a
+ * bad magic, size or checksum is CSVB200_ERR_INVALID_CSV_FORMAT; an unreadable one CSVB200_ERR_IO. */
+int csvb200_index_load(csvb200_ctx* ctx, const char* path, csvb200_index** out);
+
 /* ---- K1 known-answer exports (debug) -------------------------------------------------------- */
 /* per 64-byte block: quote_bits / all_struct as get_struct_positions(16 | 3) (src/avx/stage1.rs:392,394) */
 int csvb200_block_masks(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* quote_words,

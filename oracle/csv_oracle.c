@@ -523,6 +523,34 @@ int oracle_chunks(uint32_t record_cnt, uint64_t jump, uint8_t num, oracle_chunk 
 }
 
 /* src/lib.rs:139-152 blsr identity: x & (x - 1) clears the lowest set bit. */
+/* src/reader.rs:26-132 is_ascii ("Non-core", word-at-a-time): scalar loop for short inputs (:54-61),
+ * first word read unaligned (:72-77), aligned words up to len - 8 (:94-118), last word read unaligned
+ * (:130-134).  usize = u64. */
+int oracle_is_ascii(const uint8_t *s, size_t len)
+{
+    const uint64_t mask = 0x8080808080808080ull;            /* :29-31 */
+    const size_t W = 8;
+    size_t align_offset = (size_t)((W - ((uintptr_t)s & (W - 1))) & (W - 1));
+    if (len < W || len < align_offset) {                    /* :54-61 */
+        for (size_t i = 0; i < len; ++i)
+            if (s[i] >= 128) return 0;
+        return 1;
+    }
+    const size_t offset_to_aligned = align_offset == 0 ? W : align_offset;   /* :65-69 */
+    uint64_t w;
+    memcpy(&w, s, W);                                       /* :74 read_unaligned */
+    if (w & mask) return 0;
+    size_t byte_pos = offset_to_aligned;
+    while (byte_pos + W <= len) {                           /* :94 byte_pos <= len - USIZE_SIZE */
+        memcpy(&w, s + byte_pos, W);
+        if (w & mask) return 0;
+        byte_pos += W;
+    }
+    if (byte_pos == len) return 1;                          /* :122-124 */
+    memcpy(&w, s + len - W, W);                             /* :130-132 */
+    return (w & mask) == 0;
+}
+
 /* ---- definitions BEYOND the reference (SURVEY 8f "next" rows) -------------------------------------
  * The reference has no counterpart for these, so there is nothing to pin them to: they are scalar
  * statements of the definitions in include/csvb200.h, used to check the CUDA kernels.  "parity unpinned". */

@@ -63,6 +63,7 @@ int oracle_seek_fields_timed(const uint64_t *index, size_t index_len, size_t dat
                              uint64_t *checksum, uint64_t *hits);
 int oracle_boundaries(uint32_t task_size, uint8_t job_count, oracle_boundary *out);
 int oracle_chunks(uint32_t record_cnt, uint64_t jump, uint8_t num, oracle_chunk *out);
+int oracle_is_ascii(const uint8_t *s, size_t len);
 /* definitions beyond the reference (see csv_oracle.c) */
 uint64_t oracle_tape_first_bad_slot(const uint8_t *bytes, size_t n, const uint64_t *index,
                                     size_t index_len, uint32_t field_cnt, int crlf);

@@ -96,6 +96,7 @@ def lib():
                                                 C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                                 C.c_void_p]
         L.oracle_materialize_column.restype = C.c_uint64
+        L.oracle_is_ascii.argtypes = [C.c_void_p, C.c_size_t]
         L.oracle_blsr.argtypes = [C.c_uint64]
         L.oracle_blsr.restype = C.c_uint64
         _lib = L
@@ -278,6 +279,24 @@ def materialize_column(data, index: np.ndarray, record_cnt: int, field_cnt: int,
     out = np.zeros(max(int(total), 1), dtype=np.uint8)
     lib().oracle_materialize_column(*args, out.ctypes.data)
     return offs, out[:int(total)].tobytes()
+
+
+def is_ascii(data) -> bool:
+    """reader::is_ascii (src/reader.rs:26-132)."""
+    a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data)
+    if a.size == 0:
+        return True
+    return bool(lib().oracle_is_ascii(a.ctypes.data, a.size))
+
+
+def utf8_valid_up_to(data):
+    """core::str::from_utf8(data): None when well-formed, else Utf8Error::valid_up_to().  CPython's strict
+    decoder implements the same Unicode well-formedness table and reports the same start position."""
+    try:
+        bytes(data).decode("utf-8")
+        return None
+    except UnicodeDecodeError as e:
+        return e.start
 
 
 def blsr(x: int) -> int:

@@ -690,3 +690,85 @@ def test_index_build_file_vs_oracle(ctx):
         assert got.tolist() == [0]
     with pytest.raises(cs.Io):
         ctx.index_build_file("/nonexistent/definitely_missing.csv")
+
+
+# ---- input validation and the on-disk index ---------------------------------------
+def test_validate_utf8_vs_python_decoder(ctx):
+    good = "id,name\n1,héllo\n2,wörld – ✓\n3,🙂🙂\n".encode() * 3000
+    assert ctx.validate_utf8(good) == (None, False)
+    assert ctx.validate_utf8(b"a,b\n1,2\n" * 50000) == (None, True)
+    assert ctx.validate_utf8(b"") == (None, True)
+    crafted = [b"ab\xe2\x82", b"ab\xc0\xaf", b"\xed\xa0\x80", b"a\x80", b"\xf4\x90\x80\x80", b"\xf0\x8f\xbf\xbf",
+               b"\xe0\x9f\xbf", b"\xc2", b"x\xf0\x9f\x99", b"\xf5\x80\x80\x80", b"\xff", b"\xc2\x80\x80",
+               b"\xe1\x80\xc2\x80", b"ok\xe2\x82\xac\xe2\x82\xac\x80", b"\xf0\x9f\x99\x82" * 5 + b"\xbf"]
+    for c in crafted:
+        for pad in (0, 1, 13, 14, 15, 16, 17, 31, 4093):     # every position relative to the 16-byte chunks
+            for tail in (b"", b"tail,more\n"):
+                data = b"x" * pad + c + tail
+                want = O.utf8_valid_up_to(data)
+                got, asc = ctx.validate_utf8(data)
+                assert got == want, (c, pad, tail, got, want)
+                assert asc == O.is_ascii(data) == False  # noqa: E712
+    rng = np.random.default_rng(5)
+    alphabet = np.array([0x41, 0x2C, 0x0A, 0x80, 0xBF, 0xC2, 0xC1, 0xE0, 0xA0, 0x9F, 0xED, 0xEF, 0xF0, 0x90, 0x8F, 0xF4,
+                         0xF5, 0xE2, 0x82, 0xAC], dtype=np.uint8)
+    for seed in range(60):
+        n = int(rng.integers(1, 3000))
+        # mostly ASCII with bursts of bytes from the tricky alphabet
+        data = np.full(n, 0x61, dtype=np.uint8)
+        k = int(rng.integers(0, 12))
+        pos = rng.integers(0, n, size=k)
+        for p_ in pos:
+            seg = alphabet[rng.integers(0, alphabet.size, size=int(rng.integers(1, 6)))]
+            data[p_:p_ + seg.size] = seg[:max(0, min(seg.size, n - p_))]
+        raw = data.tobytes()
+        got, asc = ctx.validate_utf8(raw)
+        assert got == O.utf8_valid_up_to(raw), (seed, raw)
+        assert asc == O.is_ascii(raw)
+    # valid multi-byte text stays valid wherever the chunk boundaries fall
+    txt = "αβγ,δεζ\nκόσμε,🙂\n".encode()
+    for pad in range(0, 40):
+        assert ctx.validate_utf8(b"y" * pad + txt * 100)[0] is None
+
+
+def test_index_save_load_roundtrip(ctx):
+    raw = golden_bytes("sample_rx.csv")
+    idx = ctx.index_build(raw, cs.BUILD_KEEP_BYTES)
+    rc, jump = idx.tape_init(8, True)
+    want = idx.to_host().copy()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "rx.idx")
+        idx.save(path)
+        assert os.path.getsize(path) == 64 + 8 * want.size
+        blob = open(path, "rb").read()
+        assert blob[:8] == b"CSVB2IDX" and np.frombuffer(blob[64:], dtype="<u8").tolist() == want.tolist()
+        got = ctx.index_load(path)
+        assert (got.to_host() == want).all() and got.end_parity == idx.end_parity
+        assert got.seek_field(1, 2) == idx.seek_field(1, 2) and got.seek_record(6) == idx.seek_record(6)
+        assert got.seek_field(6, 8) is None
+        with pytest.raises(cs.InvalidState):
+            got.tape_validate(8, True)           # needs the input bytes, which a loaded index does not have
+        got.free()
+        # an index saved before tape_init loads without Tape metadata
+        idx2 = ctx.index_build(raw)
+        idx2.save(path)
+        got = ctx.index_load(path)
+        with pytest.raises(cs.InvalidState):
+            got.seek_record(0)
+        got.free()
+        idx2.free()
+        # corruption is detected
+        bad = bytearray(blob)
+        bad[70] ^= 1
+        open(path, "wb").write(bytes(bad))
+        with pytest.raises(cs.InvalidCsvFormat):
+            ctx.index_load(path)
+        open(path, "wb").write(blob[:-8])
+        with pytest.raises(cs.InvalidCsvFormat):
+            ctx.index_load(path)
+        open(path, "wb").write(b"NOTANIDX" + blob[8:])
+        with pytest.raises(cs.InvalidCsvFormat):
+            ctx.index_load(path)
+        with pytest.raises(cs.Io):
+            ctx.index_load(os.path.join(d, "missing.idx"))
+    idx.free()

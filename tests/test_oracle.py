@@ -165,3 +165,28 @@ def test_tape_first_bad_slot_known_answers():
         assert O.tape_first_bad_slot(raw, O.read_sse(raw), fc, crlf) == 0xFFFFFFFFFFFFFFFF
     raw = golden_bytes("reader_test01.csv")                        # ragged last row
     assert O.tape_first_bad_slot(raw, O.read_sse(raw), 3, False) != 0xFFFFFFFFFFFFFFFF
+
+
+def test_is_ascii_restatement():
+    rng = np.random.default_rng(11)
+    for n in list(range(0, 40)) + [63, 64, 65, 1000, 4097]:
+        base = rng.integers(0, 128, size=n, dtype=np.uint8)
+        for off in (0, 1, 3, 7):           # every alignment of the slice start
+            buf = np.zeros(n + 16, dtype=np.uint8)
+            buf[off:off + n] = base
+            view = buf[off:off + n]
+            assert O.is_ascii(view) is True
+            for hit in {0, n // 2, n - 1} if n else ():
+                view[hit] |= 0x80
+                assert O.is_ascii(view) is False, (n, off, hit)
+                view[hit] &= 0x7F
+
+
+def test_utf8_valid_up_to_known_answers():
+    assert O.utf8_valid_up_to(b"plain ascii") is None
+    assert O.utf8_valid_up_to("héllo, wörld – ✓ 🙂".encode()) is None
+    assert O.utf8_valid_up_to(b"ab\xe2\x82") == 2            # truncated at the end
+    assert O.utf8_valid_up_to(b"ab\xc0\xaf") == 2            # overlong lead C0
+    assert O.utf8_valid_up_to(b"\xed\xa0\x80") == 0          # surrogate
+    assert O.utf8_valid_up_to(b"a\x80") == 1                 # stray continuation
+    assert O.utf8_valid_up_to(b"\xf4\x90\x80\x80") == 0      # > U+10FFFF
