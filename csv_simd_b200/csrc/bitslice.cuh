@@ -45,6 +45,24 @@ CSVB_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 #endif
 }
 
+// count trailing / leading zeros of a non-zero word
+CSVB_HD int ctz32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+CSVB_HD int clz32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)v);
+#else
+    return __builtin_clz(v);
+#endif
+}
+
 struct Masks32 {
     uint32_t quote;  // bit i set <=> byte i == '"'
     uint32_t sep;    // bit i set <=> byte i in {',', CR, LF}
@@ -75,10 +93,10 @@ CSVB_HD void delta_swap_pair(uint32_t& a, uint32_t& b)
     b = nb;
 }
 
-// w[0..7]: the 32 bytes in memory order (little-endian words).
-CSVB_HD Masks32 classify32(const uint32_t w[8])
+// w[0..7]: the 32 bytes in memory order (little-endian words).  x[b] <- bit-plane b in natural order:
+// bit i of x[b] = bit b of byte i.  16 PRMT + 3 delta-swap rounds.
+CSVB_HD void bitplanes32(const uint32_t w[8], uint32_t x[8])
 {
-    uint32_t x[8];
     // 1) byte transpose: x[j] byte k = input byte 8k + j   (two 4x4 byte transposes)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -104,6 +122,12 @@ CSVB_HD Masks32 classify32(const uint32_t w[8])
     delta_swap_pair<1, 0x55555555u>(x[2], x[3]);
     delta_swap_pair<1, 0x55555555u>(x[4], x[5]);
     delta_swap_pair<1, 0x55555555u>(x[6], x[7]);
+}
+
+CSVB_HD Masks32 classify32(const uint32_t w[8])
+{
+    uint32_t x[8];
+    bitplanes32(w, x);
     const uint32_t P0 = x[0], P1 = x[1], P2 = x[2], P3 = x[3];
     const uint32_t P4 = x[4], P5 = x[5], P6 = x[6], P7 = x[7];
     // 3) boolean membership on the planes (ptxas fuses these into 8 LOP3):

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) tape_validate_kernel(const TapeValidatePa
     // kUnroll rows are in flight together: the byte load depends on the index load, so the loop is
     // latency-bound without them (0.62 -> measured again in profiles/).
     constexpr int kUnroll = 4;
-    constexpr uint64_t kRun = 32 * 64;
+    constexpr uint64_t kRun = 32 * 16;
     for (uint64_t run = warp0 * kRun; run < last; run += warps * kRun) {
         const uint64_t run_end = run + kRun < last ? run + kRun : last;
         uint64_t k = (run + lane) % jump;             // slot s = 1 + run + lane  ->  k = (s - 1) % jump
@@ -109,7 +109,7 @@ cudaError_t launch_tape_validate(const TapeValidateParams& p, cudaStream_t strea
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    uint64_t blocks = (p.index_len + 32 * 64 * 8 - 1) / (32 * 64 * 8);   // 8 warps per block, one run each
+    uint64_t blocks = (p.index_len + 32 * 16 * 8 - 1) / (32 * 16 * 8);   // 8 warps per block, one run each
     const uint64_t max_blocks = (uint64_t)sms * 8;
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks == 0) blocks = 1;

@@ -54,3 +54,119 @@ def test_bitslice_classifier_on_host():
                                "-o", exe])
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout + out.stderr
+
+
+UTF8_HARNESS = r"""
+#include "utf8slice.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+using namespace csvb200;
+
+// scalar statement of Unicode table 3-7 (what core::str::from_utf8 checks): start of the first ill-formed
+// sequence, or -1
+static long scalar_valid_up_to(const uint8_t* s, long n)
+{
+    long i = 0;
+    while (i < n) {
+        const uint8_t b = s[i];
+        if (b < 0x80) { ++i; continue; }
+        int len; uint8_t lo = 0x80, hi = 0xBF;
+        if (b >= 0xC2 && b <= 0xDF) len = 2;
+        else if (b >= 0xE0 && b <= 0xEF) { len = 3; if (b == 0xE0) lo = 0xA0; if (b == 0xED) hi = 0x9F; }
+        else if (b >= 0xF0 && b <= 0xF4) { len = 4; if (b == 0xF0) lo = 0x90; if (b == 0xF4) hi = 0x8F; }
+        else return i;
+        if (i + 1 >= n || s[i + 1] < lo || s[i + 1] > hi) return i;
+        for (int k = 2; k < len; ++k)
+            if (i + k >= n || (s[i + k] & 0xC0) != 0x80) return i;
+        i += len;
+    }
+    return -1;
+}
+
+// the kernel's decomposition: 32-byte groups, each judged with utf8_check32 + its halos, minimum of the starts
+static long sliced_valid_up_to(const uint8_t* s, long n)
+{
+    long best = -1;
+    for (long i0 = 0; i0 < n; i0 += 32) {
+        uint8_t g[32] = {0};
+        memcpy(g, s + i0, (size_t)((n - i0) < 32 ? (n - i0) : 32));
+        uint32_t w[8];
+        memcpy(w, g, 32);
+        const uint32_t b1 = i0 >= 1 ? s[i0 - 1] : 0, b2 = i0 >= 2 ? s[i0 - 2] : 0, b3 = i0 >= 3 ? s[i0 - 3] : 0;
+        const uint32_t n0 = i0 + 32 < n ? s[i0 + 32] : 0x100, n1 = i0 + 33 < n ? s[i0 + 33] : 0x100,
+                       n2 = i0 + 34 < n ? s[i0 + 34] : 0x100;
+        const uint32_t r = utf8_check32(w, utf8_owed(b1, b2, b3), n0, n1, n2);
+        if (r != kUtf8None && (best < 0 || i0 + r < best)) best = i0 + r;
+    }
+    return best;
+}
+
+int main() {
+    srand(7);
+    long bad = 0, checked = 0;
+    const uint8_t alpha[] = {0x41, 0x2C, 0x0A, 0x7F, 0x80, 0x8F, 0x90, 0x9F, 0xA0, 0xBF, 0xC0, 0xC1, 0xC2, 0xDF, 0xE0, 0xE1,
+                             0xEC, 0xED, 0xEE, 0xEF, 0xF0, 0xF1, 0xF3, 0xF4, 0xF5, 0xF8, 0xFF};
+    const int na = (int)sizeof(alpha);
+    // exhaustive over 1..3 byte strings from the tricky alphabet at every offset around the group boundary
+    for (int len = 1; len <= 4; ++len) {
+        long combos = 1;
+        for (int k = 0; k < len; ++k) combos *= na;
+        for (long c = 0; c < combos; ++c) {
+            uint8_t seq[4];
+            long t = c;
+            for (int k = 0; k < len; ++k) { seq[k] = alpha[t % na]; t /= na; }
+            for (int pad = 27; pad <= 33; ++pad) {
+                for (int tail = 0; tail <= 1; ++tail) {
+                    std::vector<uint8_t> s((size_t)pad, 'x');
+                    s.insert(s.end(), seq, seq + len);
+                    if (tail) s.insert(s.end(), 5, 'y');
+                    const long a = scalar_valid_up_to(s.data(), (long)s.size()), b = sliced_valid_up_to(s.data(), (long)s.size());
+                    if (a != b && bad++ < 5) {
+                        printf("mismatch len=%d pad=%d tail=%d scalar=%ld sliced=%ld:", len, pad, tail, a, b);
+                        for (int k = 0; k < len; ++k) printf(" %02x", seq[k]);
+                        printf("\n");
+                    }
+                    ++checked;
+                }
+            }
+        }
+    }
+    // random mixtures, all lengths
+    for (int it = 0; it < 200000; ++it) {
+        const int n = 1 + rand() % 150;
+        std::vector<uint8_t> s((size_t)n);
+        const int mode = rand() % 3;
+        for (int i = 0; i < n; ++i)
+            s[(size_t)i] = mode == 0 ? (uint8_t)rand() : (rand() % 4 ? 'a' : alpha[rand() % na]);
+        const long a = scalar_valid_up_to(s.data(), n), b = sliced_valid_up_to(s.data(), n);
+        if (a != b && bad++ < 5) printf("random mismatch n=%d scalar=%ld sliced=%ld\n", n, a, b);
+        ++checked;
+    }
+    // well-formed text of every sequence length stays well-formed at every alignment
+    const char* txt = "a\xc3\xa9\xe2\x82\xac\xf0\x9f\x99\x82z\xed\x9f\xbf\xee\x80\x80\xf4\x8f\xbf\xbf\xe0\xa0\x80\xf0\x90\x80\x80";
+    for (int pad = 0; pad < 70; ++pad) {
+        std::vector<uint8_t> s((size_t)pad, 'x');
+        for (int r = 0; r < 6; ++r) s.insert(s.end(), (const uint8_t*)txt, (const uint8_t*)txt + strlen(txt));
+        if (scalar_valid_up_to(s.data(), (long)s.size()) != -1 || sliced_valid_up_to(s.data(), (long)s.size()) != -1) ++bad;
+        ++checked;
+    }
+    printf("checked=%ld bad=%ld\n", checked, bad);
+    return bad != 0;
+}
+"""
+
+
+def test_utf8_slice_on_host():
+    """utf8slice.cuh (the K7 kernel's rule engine) on the CPU against the scalar table 3-7 rule: exhaustive
+    over short strings from the boundary-value alphabet at every offset around a 32-byte group edge, plus
+    random mixtures.  (tests/test_oracle.py pins the same scalar rule to CPython's decoder.)"""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "u.cpp")
+        with open(src, "w") as f:
+            f.write(UTF8_HARNESS)
+        exe = os.path.join(d, "u")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "csv_simd_b200", "csrc"), src, "-o", exe])
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout[-2000:]
