@@ -273,6 +273,10 @@ int csvb200_ctx_create(int device, csvb200_ctx** out)
         if (std::strcmp(k, "tma") == 0) ctx->kernel_override = 2;
     }
     if (const char* t = std::getenv("CSVB200_TUNE")) ctx->tune = (uint32_t)std::atoi(t);
+    if (const char* t = std::getenv("CSVB200_E2E_CHUNK_MB")) {
+        const long mb = std::atol(t);
+        if (mb >= 1 && mb <= 4096) ctx->e2e_chunk = (size_t)mb << 20;
+    }
     auto bail = [&](cudaError_t) {
         cudaGetLastError();
         csvb200_ctx_destroy(ctx);
@@ -491,6 +495,7 @@ int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
                                 size_t* len_out)
 {
     if (!ctx || !len_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    const size_t kE2eChunk = ctx ? ctx->e2e_chunk : csvb200::kE2eChunk;
     const size_t nchunks = (n + kE2eChunk - 1) / kE2eChunk;
     if (nchunks < 2 || nchunks + 1 >= kRingCells || !dst) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);
     CU_TRY(ctx, cudaSetDevice(ctx->device));

@@ -38,6 +38,7 @@ struct csvb200_ctx {
     uint64_t launches = 0;
     int kernel_override = 0;  // 0 = auto, 1 = simple, 2 = tma (CSVB200_KERNEL)
     uint32_t tune = 0;        // CSVB200_TUNE experiment knob
+    size_t e2e_chunk = csvb200::kE2eChunk;   // granularity of the host -> host pipeline (CSVB200_E2E_CHUNK_MB)
     std::string err;
 };
 
