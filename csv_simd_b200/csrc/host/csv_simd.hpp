@@ -412,6 +412,42 @@ public:
         out[0] = Chunk{out[0].id, record_jump, out[0].end, out[0].record_cnt - 1, out[0].index};  // :117-123
         return out;
     }
+    // ---- beyond the crate, same device-resident tape ----
+    // which row breaks the fixed-width assumption TapeCore::init only counts on (:327)
+    csvb200_tape_report validate() const
+    {
+        csvb200_tape_report rep{};
+        check(csvb200_tape_validate(index_.raw(), header_info.field_cnt, header_info.new_line == NewLine::CRLF, &rep), index_.ctx());
+        return rep;
+    }
+    // a whole column of seek_field values (record 0 = first row after the header), trimmed / unquoted
+    struct Column {
+        std::vector<uint64_t> offsets;   // nrec + 1
+        std::string bytes;
+        std::string_view operator[](size_t i) const { return std::string_view(bytes).substr(offsets[i], offsets[i + 1] - offsets[i]); }
+        size_t size() const { return offsets.empty() ? 0 : offsets.size() - 1; }
+    };
+    Column column(uint32_t field_idx, uint32_t first_record, uint32_t nrec, uint32_t flags = CSVB200_FIELD_UNQUOTE | CSVB200_FIELD_TRIM) const
+    {
+        Column c;
+        c.offsets.assign(static_cast<size_t>(nrec) + 1, 0);
+        size_t total = 0;
+        int rc = csvb200_materialize_column(index_.raw(), field_idx, first_record, nrec, flags, c.offsets.data(), nullptr, 0, &total);
+        if (rc != CSVB200_ERR_CAPACITY) check(rc, index_.ctx());
+        c.bytes.resize(total);
+        if (total)
+            check(csvb200_materialize_column(index_.raw(), field_idx, first_record, nrec, flags, c.offsets.data(),
+                                             reinterpret_cast<uint8_t*>(&c.bytes[0]), total, &total), index_.ctx());
+        return c;
+    }
+    // core::str::from_utf8 over the whole file: nullopt = well-formed (seek_record hands out &str unchecked, record_source.rs:97-101)
+    std::optional<uint64_t> utf8_valid_up_to() const
+    {
+        uint64_t v = 0;
+        int ascii = 0;
+        check(csvb200_validate_utf8(index_.ctx(), bytes_.data(), bytes_.len(), &v, &ascii), index_.ctx());
+        return bytes_.len() == 0 || v == UINT64_MAX ? std::nullopt : std::optional<uint64_t>(v);
+    }
     const StructureIndex& index() const override { return index_; }
     const Mmap& bytes() const { return bytes_; }
     const std::vector<std::string>& header() const { return header_info.header; }

@@ -122,6 +122,29 @@ int csvsimd_tape_chunks(void* t, uint8_t num, uint64_t* out4, size_t cap, size_t
         }
     });
 }
+int csvsimd_tape_validate(void* t, csvb200_tape_report* out)
+{
+    return guard([&] { *out = static_cast<Tape*>(t)->validate(); });
+}
+// column as packed bytes: offsets[nrec + 1]; returns the total through total_out, copies min(total, cap) bytes
+int csvsimd_tape_column(void* t, uint32_t field_idx, uint32_t first_record, uint32_t nrec, uint32_t flags, uint64_t* offsets,
+                        uint8_t* dst, size_t cap, size_t* total_out)
+{
+    return guard([&] {
+        const Tape::Column c = static_cast<Tape*>(t)->column(field_idx, first_record, nrec, flags);
+        std::memcpy(offsets, c.offsets.data(), c.offsets.size() * sizeof(uint64_t));
+        *total_out = c.bytes.size();
+        std::memcpy(dst, c.bytes.data(), c.bytes.size() < cap ? c.bytes.size() : cap);
+    });
+}
+int csvsimd_tape_utf8(void* t, uint64_t* valid_up_to, int* well_formed)
+{
+    return guard([&] {
+        const auto v = static_cast<Tape*>(t)->utf8_valid_up_to();
+        *well_formed = v ? 0 : 1;
+        *valid_up_to = v ? *v : 0;
+    });
+}
 // boundaries (no GPU needed): returns count (0 = None)
 int csvsimd_boundaries(uint32_t task_size, uint8_t job_count, uint64_t* out2, size_t cap)
 {

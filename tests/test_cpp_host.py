@@ -40,6 +40,11 @@ def shim():
     L.csvsimd_boundaries.argtypes = [C.c_uint32, C.c_uint8, C.c_void_p, C.c_size_t]
     L.csvsimd_header.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), ip]
     L.csvsimd_core_seek_before_init.argtypes = [C.c_char_p]
+    from csv_simd_b200._lib import TapeReport
+    L.csvsimd_tape_validate.argtypes = [C.c_void_p, C.POINTER(TapeReport)]
+    L.csvsimd_tape_column.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                      C.c_size_t, C.POINTER(C.c_size_t)]
+    L.csvsimd_tape_utf8.argtypes = [C.c_void_p, u64p, ip]
     return L
 
 
@@ -159,3 +164,32 @@ def test_cpp_error_behaviour(shim):
         assert shim.csvsimd_core_seek_before_init(p.encode()) == INVALID_STATE   # record_source.rs:77-79
     finally:
         os.unlink(p)
+
+
+@pytest.mark.gpu
+def test_cpp_validate_column_utf8(shim):
+    """The SURVEY 8f additions through the C++ mirror: Tape::validate, Tape::column, Tape::utf8_valid_up_to."""
+    from csv_simd_b200._lib import TapeReport
+    data = golden_bytes("sample_rx.csv")
+    path = _tmp(data)
+    try:
+        t = C.c_void_p()
+        assert shim.csvsimd_create(path.encode(), C.byref(t)) == OK, shim.csvsimd_last_error()
+        rep = TapeReport()
+        assert shim.csvsimd_tape_validate(t, C.byref(rep)) == OK
+        assert rep.ok == 1 and rep.record_cnt == 8 and rep.jump == 9 and rep.first_bad_slot == 0xFFFFFFFFFFFFFFFF
+        host = O.read_sse(data)
+        for fld in (0, 2, 5, 7):
+            w_offs, w_out = O.materialize_column(data, host, 8, 8, True, fld, 0, 7, 3)
+            offs = np.zeros(8, dtype=np.uint64)
+            buf = np.zeros(4096, dtype=np.uint8)
+            total = C.c_size_t()
+            assert shim.csvsimd_tape_column(t, fld, 0, 7, 3, offs.ctypes.data, buf.ctypes.data, buf.size, C.byref(total)) == OK
+            assert (offs == w_offs).all() and buf[:total.value].tobytes() == w_out
+        v, ok = C.c_uint64(), C.c_int()
+        assert shim.csvsimd_tape_utf8(t, C.byref(v), C.byref(ok)) == OK
+        want = O.utf8_valid_up_to(data)
+        assert bool(ok.value) == (want is None) and (want is None or v.value == want)
+        shim.csvsimd_tape_free(t)
+    finally:
+        os.unlink(path)

@@ -162,3 +162,35 @@ def test_two_rank_exchange_gloo():
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True]
     assert res[0][2] == 0
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference runs the reference's CPU path (the oracle) without a GPU and prints ONE JSON
+    line with the contract's keys; under a multi-rank launch only rank 0 prints."""
+    import json
+    import subprocess
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--size", str(8 << 20)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "csv_bytes_indexed_per_sec" and d["unit"] == "GB/s"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["config"]["workload"]
+    env["RANK"] = "1"
+    env["WORLD_SIZE"] = "2"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0", "--size", str(1 << 20)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_numa_helpers():
+    from csv_simd_b200 import numa
+    assert numa._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert numa._parse_cpulist("") == []
+    assert numa.device_numa_node("0000:ff:1f.7") in (None, 0, 1, 2, 3, 4, 5, 6, 7)
