@@ -313,11 +313,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     def step_e2e():
         if world == 1:
             return ctx.index_build_to_host(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel())
-        d_in[:n].copy_(h_in, non_blocking=True)
-        sh = csd.sharded_index_build(ctx, d_in.data_ptr(), n, goff)
-        ln = len(sh.local)
-        sh.local.copy_out_ptr(h_out.data_ptr(), h_out.numel())
-        sh.local.free()
+        ln, _base, _total, _redone = csd.sharded_index_build_to_host(ctx, h_in.data_ptr(), n, goff, h_out.data_ptr(),
+                                                                      h_out.numel())
         return ln
 
     for _ in range(2):
@@ -366,7 +363,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "e2e": {"value": e2e_gbs, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8 * E_local,
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "api": "csvb200_index_build_to_host" if world == 1 else
-                           "H2D + csv_simd_b200.dist.sharded_index_build + csvb200_index_copy_out"},
+                           "csvb200_shard_build_to_host + all_gather + csvb200_shard_job_verify (csv_simd_b200.dist.sharded_index_build_to_host)"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -200,6 +200,24 @@ class Context:
             C.c_void_p(d_result_out), C.byref(h)))
         return StructureIndex(self, h)
 
+    def shard_build_to_host(self, host_ptr: int, n: int, shard_rank: int, global_offset: int, emit_sentinel: bool,
+                            dst_ptr: int, dst_cap: int, d_result_out: int):
+        """csvb200_shard_build_to_host -> (entries written to dst, job handle for shard_job_verify)."""
+        ln, job = C.c_size_t(), C.c_void_p()
+        self._check(self._lib.csvb200_shard_build_to_host(self._h, C.c_void_p(host_ptr), n, shard_rank, global_offset,
+                                                          int(emit_sentinel), C.c_void_p(dst_ptr), dst_cap, C.byref(ln),
+                                                          C.c_void_p(d_result_out), C.byref(job)))
+        return ln.value, job
+
+    def shard_job_verify(self, job, d_gathered: int, world: int, d_final_out: int = 0):
+        """-> (final entry count in dst, whether the shard had to be re-indexed); frees the job."""
+        ln, redone = C.c_size_t(), C.c_int()
+        rc = self._lib.csvb200_shard_job_verify(job, C.c_void_p(d_gathered), world, C.c_void_p(d_final_out or 0),
+                                                C.byref(ln), C.byref(redone))
+        self._lib.csvb200_shard_job_free(job)
+        self._check(rc)
+        return ln.value, bool(redone.value)
+
     # -- input validation / on-disk index ------------------------------------------------------
     def validate_utf8(self, data):
         """(valid_up_to or None when well-formed UTF-8, is_ascii) -- csvb200_validate_utf8."""

@@ -486,63 +486,90 @@ static int build_to_host_serial(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
     return rc;
 }
 
-// End-to-end pipeline: the input goes up in kE2eChunk pieces, each piece is indexed by its own launch
+// End-to-end pipeline: the input goes up in e2e_chunk pieces, each piece is indexed by its own launch
 // chained to the previous one through a device-resident carry cell {entries so far, quote parity}
 // (no host round trip between launches), and every finished index segment goes down on a second
 // stream while later pieces are still going up -- PCIe is full duplex, so the step costs about
 // max(H2D, D2H) instead of their sum.
-int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap,
-                                size_t* len_out)
+namespace {
+struct PipeOpts {
+    uint64_t pos_bias = 0;           // global byte offset of host_bytes[0] (shards)
+    int emit_sentinel = 1;
+    bool predict = false;            // shard, first attempt: guess the carry-in parity from the bytes of chunk 0
+    const uint64_t* d_carry0 = nullptr;   // shard, second attempt: device cell {0, true carry parity}
+    uint64_t* d_result4 = nullptr;   // optional device words {entries excl. sentinel, end parity, carry used, separator total}
+    const uint8_t* d_bytes_in = nullptr;  // the bytes are already on the device (rebuild): no uploads
+    uint8_t** keep_bytes = nullptr;  // receives the device copy of the input instead of freeing it
+};
+
+// overflow_out: the index reserve was too small (the caller decides how to rebuild); dst_small_out (optional):
+// the caller's array was too small (*len_out says how many entries there are) -- an error when it is null
+int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap, size_t* len_out,
+                     const PipeOpts& o, bool* overflow_out, bool* dst_small_out = nullptr)
 {
-    if (!ctx || !len_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
-    const size_t kE2eChunk = ctx ? ctx->e2e_chunk : csvb200::kE2eChunk;
-    const size_t nchunks = (n + kE2eChunk - 1) / kE2eChunk;
-    if (nchunks < 2 || nchunks + 1 >= kRingCells || !dst) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);
+    const size_t chunk = ctx->e2e_chunk;
+    const size_t nchunks = std::max<size_t>(1, (n + chunk - 1) / chunk);
+    if (nchunks + 1 >= kRingCells) return fail(ctx, CSVB200_ERR_INVALID_ARG, "input too large for the chunk pipeline");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s_up = ctx->stream, s_down = ctx->copy_stream;
-    uint8_t* d_bytes = nullptr;
+    uint8_t* d_bytes = const_cast<uint8_t*>(o.d_bytes_in);
     uint64_t* d_index = nullptr;
     const size_t cap = initial_cap(ctx, n);
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, s_up));
+    const uint64_t out_base = o.emit_sentinel ? 1 : 0;
+    if (!d_bytes) CU_TRY(ctx, cudaMallocAsync((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, s_up));
     CU_TRY(ctx, cudaMallocAsync((void**)&d_index, cap * sizeof(uint64_t), s_up));
-    CU_TRY(ctx, cudaMemsetAsync(d_index, 0, sizeof(uint64_t), s_up));  // sentinel (src/reader.rs:216)
-    // cells: cell0 = carry into chunk 0 = {0, 0}; cell[c+1] = result of chunk c
+    if (out_base) CU_TRY(ctx, cudaMemsetAsync(d_index, 0, sizeof(uint64_t), s_up));  // sentinel (src/reader.rs:216)
+    // cells: cell0 = carry into chunk 0; cell[c+1] = result of chunk c
     const size_t cell0 = ctx->next_cell + nchunks + 1 <= kRingCells ? ctx->next_cell : 0;
     ctx->next_cell = (cell0 + nchunks + 1) % kRingCells;
     uint64_t* d_cells = ctx->d_cells + cell0 * kCellWords;
     uint64_t* h_cells = ctx->h_cells + cell0 * kCellWords;
-    CU_TRY(ctx, cudaMemsetAsync(d_cells, 0, kCellWords * sizeof(uint64_t), s_up));
+    if (o.d_carry0)
+        CU_TRY(ctx, cudaMemcpyAsync(d_cells, o.d_carry0, 2 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s_up));
+    else
+        CU_TRY(ctx, cudaMemsetAsync(d_cells, 0, kCellWords * sizeof(uint64_t), s_up));
+    if (o.d_result4) CU_TRY(ctx, cudaMemsetAsync(o.d_result4, 0, 4 * sizeof(uint64_t), s_up));
     std::vector<cudaEvent_t> done(nchunks, nullptr);
     int rc = CSVB200_OK;
     auto cleanup = [&]() {
         for (cudaEvent_t e : done)
             if (e) cudaEventDestroy(e);
         cudaStreamSynchronize(s_down);
-        cudaFreeAsync(d_bytes, s_up);
+        if (o.keep_bytes && rc == CSVB200_OK)
+            *o.keep_bytes = d_bytes;
+        else if (!o.d_bytes_in)
+            cudaFreeAsync(d_bytes, s_up);
         cudaFreeAsync(d_index, s_up);
     };
     // ---- enqueue every upload + launch; nothing here waits on the host ----
     for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
-        const size_t off = c * kE2eChunk, len = std::min(kE2eChunk, n - off);
-        rc = upload(ctx, d_bytes + off, host_bytes + off, len);
+        const size_t off = c * chunk, len = std::min(chunk, n - off);
+        if (!o.d_bytes_in) rc = upload(ctx, d_bytes + off, host_bytes + off, len);
         if (rc) break;
-        const uint64_t num_tiles = (len + kTileBytes - 1) / kTileBytes;
+        cudaError_t e = cudaSuccess;
+        if (c == 0 && o.predict && len > 0) {
+            e = launch_predict_carry(d_bytes, len, kDefaultPredictWindow, d_cells, s_up);   // cell0 <- {0, guess, found, 0}
+            ctx->launches += 1;
+        }
+        const uint64_t num_tiles = std::max<uint64_t>(1, (len + kTileBytes - 1) / kTileBytes);   // an empty shard runs one empty tile
         const size_t sbytes = 128 + num_tiles * kDescStride * sizeof(uint64_t);
         rc = ensure_scratch(ctx, sbytes);
         if (rc) break;
-        cudaError_t e = cudaMemsetAsync(ctx->d_scratch, 0, sbytes, s_up);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_scratch, 0, sbytes, s_up);
         BuildParams p{};
         p.in = d_bytes + off;
         p.n = len;
         p.index = d_index;
         p.cap = cap;
-        p.out_base = 1;
-        p.pos_bias = off;
+        p.out_base = out_base;
+        p.pos_bias = o.pos_bias + off;
         p.carry = d_cells + c * kCellWords;
         p.num_tiles = (uint32_t)num_tiles;
         p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
         p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
         p.result = d_cells + (c + 1) * kCellWords;
+        p.result2_words = 2;
+        if (o.d_result4) p.total_out = reinterpret_cast<unsigned long long*>(o.d_result4 + 3);
         p.tune = ctx->tune;
         bool use_tma = tma_path_usable(len);
         if (ctx->kernel_override == 1) use_tma = false;
@@ -558,15 +585,25 @@ int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
             rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
         }
     }
+    if (rc == CSVB200_OK && o.d_result4) {
+        // {entries, end parity} of the last chunk, the carry parity the first chunk used; the separator total was
+        // accumulated by the launches themselves
+        cudaError_t e = cudaMemcpyAsync(o.d_result4, d_cells + nchunks * kCellWords, 2 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s_up);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(o.d_result4 + 2, d_cells + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s_up);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
+        }
+    }
     // ---- as each chunk's kernel finishes, send its index segment down on the second stream ----
     size_t copied = 0;  // entries already on their way to dst (including the sentinel)
     bool overflow = false, dst_small = false;
     for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
         cudaError_t e = cudaEventSynchronize(done[c]);
         if (e == cudaSuccess) {
-            const size_t upto = 1 + (size_t)h_cells[(c + 1) * kCellWords];  // entries through this chunk
+            const size_t upto = (size_t)out_base + (size_t)h_cells[(c + 1) * kCellWords];  // entries through this chunk
             if (upto > cap) overflow = true;
-            if (upto > dst_cap) dst_small = true;
+            if (upto > dst_cap || (upto && !dst)) dst_small = true;
             if (!overflow && !dst_small && upto > copied) {
                 e = cudaStreamWaitEvent(s_down, done[c], 0);
                 if (e == cudaSuccess)
@@ -583,13 +620,138 @@ int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
     }
     if (rc == CSVB200_OK) {
         cudaError_t e = cudaStreamSynchronize(s_down);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s_up);
         if (e != cudaSuccess) rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
     }
     cleanup();
     if (rc) return rc;
-    if (overflow) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);  // denser than the reserve
-    if (dst_small) return fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    *overflow_out = overflow;
+    if (dst_small_out) *dst_small_out = dst_small;
+    if (!overflow && dst_small && !dst_small_out) return fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
     return CSVB200_OK;
+}
+}  // namespace
+
+int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap,
+                                size_t* len_out)
+{
+    if (!ctx || !len_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    const size_t nchunks = (n + ctx->e2e_chunk - 1) / ctx->e2e_chunk;
+    if (nchunks < 2 || nchunks + 1 >= kRingCells || !dst) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);
+    bool overflow = false;
+    int rc = pipeline_to_host(ctx, host_bytes, n, dst, dst_cap, len_out, PipeOpts{}, &overflow);
+    if (rc) return rc;
+    if (overflow) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);  // denser than the reserve
+    return CSVB200_OK;
+}
+
+// ---- end-to-end form of the speculative sharded build --------------------------------------------------------
+struct csvb200_shard_job {
+    csvb200_ctx* ctx = nullptr;
+    const uint8_t* host_bytes = nullptr;
+    size_t n = 0;
+    uint32_t rank = 0;
+    uint64_t global_offset = 0;
+    int emit_sentinel = 0;
+    uint64_t* dst = nullptr;
+    size_t dst_cap = 0;
+    uint64_t* d_result4 = nullptr;
+    uint8_t* d_bytes = nullptr;     // device copy of the shard, kept until the job is verified
+    size_t carry_cell = 0;
+    size_t len = 0;                 // entries in dst after the speculative attempt
+    bool dst_small = false;         // ... which did not fit dst (only an error if the guess turns out right)
+    bool verified = false;
+};
+
+int csvb200_shard_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint32_t shard_rank,
+                                uint64_t global_offset, int emit_sentinel, uint64_t* dst, size_t dst_cap, size_t* len_out,
+                                uint64_t* d_result_out, csvb200_shard_job** job_out)
+{
+    if (!ctx || !len_out || !d_result_out || !job_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    csvb200_shard_job* job = new (std::nothrow) csvb200_shard_job();
+    if (!job) return fail(ctx, CSVB200_ERR_OOM, "host allocation failed");
+    job->ctx = ctx;
+    job->host_bytes = host_bytes;
+    job->n = n;
+    job->rank = shard_rank;
+    job->global_offset = global_offset;
+    job->emit_sentinel = emit_sentinel;
+    job->dst = dst;
+    job->dst_cap = dst_cap;
+    job->d_result4 = d_result_out;
+    job->carry_cell = ctx->next_cell;
+    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+    PipeOpts o;
+    o.pos_bias = global_offset;
+    o.emit_sentinel = emit_sentinel;
+    o.predict = shard_rank != 0;          // rank 0 starts outside quotes by definition
+    o.d_result4 = d_result_out;
+    o.keep_bytes = &job->d_bytes;
+    bool overflow = false;
+    int rc = pipeline_to_host(ctx, host_bytes, n, dst, dst_cap, len_out, o, &overflow, &job->dst_small);
+    if (!rc && overflow) {
+        // denser than the reserve: raise the reserve to the worst case for this context and go again
+        const uint32_t num = ctx->reserve_num, den = ctx->reserve_den;
+        ctx->reserve_num = 1;
+        ctx->reserve_den = 1;
+        cudaFreeAsync(job->d_bytes, ctx->stream);
+        job->d_bytes = nullptr;
+        rc = pipeline_to_host(ctx, host_bytes, n, dst, dst_cap, len_out, o, &overflow, &job->dst_small);
+        ctx->reserve_num = num;
+        ctx->reserve_den = den;
+    }
+    if (rc) {
+        if (job->d_bytes) cudaFreeAsync(job->d_bytes, ctx->stream);
+        delete job;
+        return rc;
+    }
+    job->len = *len_out;
+    *job_out = job;
+    return CSVB200_OK;
+}
+
+int csvb200_shard_job_verify(csvb200_shard_job* job, const uint64_t* d_gathered, uint32_t world, uint64_t* d_final_out,
+                             size_t* len_out, int* redone)
+{
+    if (!job || !d_gathered || !len_out) return CSVB200_ERR_INVALID_ARG;
+    csvb200_ctx* ctx = job->ctx;
+    if (job->rank >= world) return fail(ctx, CSVB200_ERR_INVALID_ARG, "bad world size");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    uint64_t* d_carry = ctx->d_cells + job->carry_cell * kCellWords;
+    uint64_t* h_carry = ctx->h_cells + job->carry_cell * kCellWords;
+    CU_TRY(ctx, launch_verify_carry(d_gathered, world, job->rank, d_carry, d_final_out, ctx->stream));
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(h_carry, d_carry, kCellWords * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    job->verified = true;
+    const bool redo = (h_carry[3] & 1u) != 0;
+    if (redone) *redone = redo ? 1 : 0;
+    *len_out = job->len;
+    if (!redo) return job->dst_small ? fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small") : CSVB200_OK;
+    // the guess was wrong: index the shard again (it is still on the device) with the true carry
+    PipeOpts o;
+    o.pos_bias = job->global_offset;
+    o.emit_sentinel = job->emit_sentinel;
+    o.d_carry0 = d_carry;
+    o.d_bytes_in = job->d_bytes;
+    o.d_result4 = job->d_result4;
+    bool overflow = false;
+    const uint32_t num = ctx->reserve_num, den = ctx->reserve_den;
+    ctx->reserve_num = 1;    // a flipped carry can turn every masked separator into an entry
+    ctx->reserve_den = 1;
+    int rc = pipeline_to_host(ctx, job->host_bytes, job->n, job->dst, job->dst_cap, len_out, o, &overflow);
+    ctx->reserve_num = num;
+    ctx->reserve_den = den;
+    return rc;
+}
+
+void csvb200_shard_job_free(csvb200_shard_job* job)
+{
+    if (!job) return;
+    cudaSetDevice(job->ctx->device);
+    if (job->d_bytes) cudaFreeAsync(job->d_bytes, job->ctx->stream);
+    cudaGetLastError();
+    delete job;
 }
 
 int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t* parity_out)

@@ -153,3 +153,23 @@ def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: i
     counts[0] += 1                                                              # sentinel lives on rank 0
     ps = [int(v) for v in pars.cpu().tolist()]
     return ShardedIndex(idx, exclusive_bases(counts)[rank], sum(counts), carry_in_parities(ps)[rank], ps)
+
+
+def sharded_index_build_to_host(ctx: api.Context, host_ptr: int, n: int, global_offset: int, dst_ptr: int, dst_cap: int,
+                                group=None):
+    """End-to-end form: this rank's shard in (pinned) host memory -> this rank's index segment in host memory
+    (csvb200_shard_build_to_host: chunked H2D, chained launches, overlapped D2H under the predicted carry), then
+    the one all_gather and csvb200_shard_job_verify.  Returns (entries in dst, base slot of the segment in the
+    global index, total length of the global index, whether this shard had to be re-indexed)."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    device = torch.device("cuda", ctx.device)
+    res_local = torch.empty(4, dtype=torch.int64, device=device)
+    _, job = ctx.shard_build_to_host(host_ptr, n, rank, global_offset, rank == 0, dst_ptr, dst_cap, res_local.data_ptr())
+    res_all = torch.empty(4 * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(res_all, res_local, group=group)
+    final = torch.empty(2 * world, dtype=torch.int64, device=device)
+    ln, redone = ctx.shard_job_verify(job, res_all.data_ptr(), world, final.data_ptr())
+    counts = [int(c) for c in final.cpu().tolist()[0::2]]
+    counts[0] += 1
+    return ln, exclusive_bases(counts)[rank], sum(counts), redone

@@ -169,6 +169,21 @@ int csvb200_index_shard_verify(csvb200_index* idx, const uint64_t* d_gathered, u
 /* diagnostics (synchronises): whether the misprediction rebuild ran, and the true carry-in parity */
 int csvb200_index_shard_redone(csvb200_index* idx, int* redone, int* carry_parity);
 
+/* End-to-end form of the speculative protocol: this rank's shard in HOST memory -> this rank's segment
+ * of the index in HOST memory, uploads / launches / downloads overlapped chunk by chunk exactly like
+ * csvb200_index_build_to_host.  The segment is produced under the predicted carry and d_result_out
+ * (4 x u64 device words, as above) is ready for the all-gather when the call returns; after the
+ * all-gather csvb200_shard_job_verify derives the true carries and counts (d_final_out, optional,
+ * world x 2 u64 device words) and, only if this shard's guess was wrong, re-indexes it from the device
+ * copy it kept and overwrites dst (*len_out updated, *redone = 1). */
+typedef struct csvb200_shard_job csvb200_shard_job;
+int csvb200_shard_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint32_t shard_rank,
+                                uint64_t global_offset, int emit_sentinel, uint64_t* dst, size_t dst_cap, size_t* len_out,
+                                uint64_t* d_result_out, csvb200_shard_job** job_out);
+int csvb200_shard_job_verify(csvb200_shard_job* job, const uint64_t* d_gathered, uint32_t world, uint64_t* d_final_out,
+                             size_t* len_out, int* redone);
+void csvb200_shard_job_free(csvb200_shard_job* job);
+
 /* ---- index object: StructureIndex (src/stage1.rs:61) --------------------------------------- */
 int csvb200_index_sync(csvb200_index* idx);
 size_t csvb200_index_len(csvb200_index* idx);          /* entries incl. the sentinel if emitted */

@@ -772,3 +772,60 @@ def test_index_save_load_roundtrip(ctx):
         with pytest.raises(cs.Io):
             ctx.index_load(os.path.join(d, "missing.idx"))
     idx.free()
+
+
+def test_shard_build_to_host_pipeline(ctx):
+    """csvb200_shard_build_to_host + csvb200_shard_job_verify: all ranks of a sharded file emulated on one GPU,
+    multi-chunk shards (64 MiB chunks), a cut inside a quoted field, a mispredicted shard that is redone."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    q, _ = gen.quoted(200 << 20, seed=49)
+    raw = q
+    want = O.read_sse(raw)
+    n = raw.size
+    blob = raw.tobytes()
+    cut1 = blob.index(b'"', n // 3) + 1                       # inside / at the edge of a quoted field
+    cuts = [0, cut1, (2 * n) // 3 + 7, n]
+    G = 3
+    res = torch.zeros((G, 4), dtype=torch.int64, device=dev)
+    outs, jobs, lens = [], [], []
+    for k in range(G):
+        shard = torch.from_numpy(raw[cuts[k]:cuts[k + 1]].copy()).pin_memory()
+        out = torch.zeros(shard.numel() // 3 + 8192, dtype=torch.int64).pin_memory()
+        ln, job = ctx.shard_build_to_host(shard.data_ptr(), shard.numel(), k, cuts[k], k == 0, out.data_ptr(), out.numel(),
+                                          res[k].data_ptr())
+        outs.append((shard, out))
+        jobs.append(job)
+        lens.append(ln)
+    final = torch.zeros((G, 2), dtype=torch.int64, device=dev)
+    got, redone = [], []
+    for k in range(G):
+        ln, rd = ctx.shard_job_verify(jobs[k], res.data_ptr(), G, final.data_ptr())
+        got.append(outs[k][1].numpy()[:ln].view(np.uint64).copy())
+        redone.append(rd)
+    full = np.concatenate(got)
+    assert full.shape == want.shape and (full == want).all()
+    assert not any(redone)
+    fin = final.cpu().tolist()
+    assert [f[0] + (k == 0) for k, f in enumerate(fin)] == [g.size for g in got]
+    # misleading data: the guess of shard 1 is wrong, the job re-indexes it from the device copy
+    raw2 = np.frombuffer((b'aa,bb"\n,cc,dd\n' * (6 << 20)) + b'x,y\n', dtype=np.uint8)
+    want2 = O.closed_form_numpy(raw2)
+    cuts2 = [0, 14 * (3 << 20) + 3, raw2.size]
+    res = torch.zeros((2, 4), dtype=torch.int64, device=dev)
+    outs, jobs = [], []
+    for k in range(2):
+        shard = torch.from_numpy(raw2[cuts2[k]:cuts2[k + 1]].copy()).pin_memory()
+        out = torch.zeros(shard.numel() // 3 + 8192, dtype=torch.int64).pin_memory()
+        ln, job = ctx.shard_build_to_host(shard.data_ptr(), shard.numel(), k, cuts2[k], k == 0, out.data_ptr(), out.numel(),
+                                          res[k].data_ptr())
+        outs.append((shard, out))
+        jobs.append(job)
+    got, redone = [], []
+    for k in range(2):
+        ln, rd = ctx.shard_job_verify(jobs[k], res.data_ptr(), 2, 0)
+        got.append(outs[k][1].numpy()[:ln].view(np.uint64).copy())
+        redone.append(rd)
+    full = np.concatenate(got)
+    assert redone == [False, True]
+    assert full.shape == want2.shape and (full == want2).all()
