@@ -314,6 +314,10 @@ void csvb200_ctx_destroy(csvb200_ctx* ctx)
     if (ctx->d_cells) cudaFree(ctx->d_cells);
     if (ctx->h_cells) cudaFreeHost(ctx->h_cells);
     if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->h_stream_in[i]) cudaFreeHost(ctx->h_stream_in[i]);
+        if (ctx->h_stream_out[i]) cudaFreeHost(ctx->h_stream_out[i]);
+    }
     for (int b = 0; b < kStageBufs; ++b) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
         if (ctx->stage_free[b]) cudaEventDestroy(ctx->stage_free[b]);
@@ -1049,6 +1053,10 @@ static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fl
     if (!direct) {
         if (ctx->seek_stage_bytes < nslots * slot_bytes) {   // page-locking is slow: keep the buffer in the context
             if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->h_stream_in[i]) cudaFreeHost(ctx->h_stream_in[i]);
+        if (ctx->h_stream_out[i]) cudaFreeHost(ctx->h_stream_out[i]);
+    }
             ctx->h_seek_stage = nullptr;
             ctx->seek_stage_bytes = 0;
             SEEK_TRY(cudaHostAlloc((void**)&ctx->h_seek_stage, nslots * slot_bytes, cudaHostAllocDefault));

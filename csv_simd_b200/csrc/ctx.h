@@ -30,6 +30,10 @@ struct csvb200_ctx {
     uint64_t* d_cells = nullptr;
     uint64_t* h_cells = nullptr;
     size_t next_cell = 0;
+    // pinned rings of the streaming ingest (stream.cu), kept across calls: page-locking 240 MiB costs ~0.1 s
+    uint8_t* h_stream_in[3] = {nullptr, nullptr, nullptr};
+    uint64_t* h_stream_out[3] = {nullptr, nullptr, nullptr};
+    size_t stream_chunk = 0, stream_out_cap = 0;
     uint8_t* h_seek_stage = nullptr;   // pinned staging of the batched seeks from pageable arrays (kept across calls)
     size_t seek_stage_bytes = 0;
     uint8_t* h_stage[csvb200::kStageBufs] = {nullptr, nullptr};

@@ -143,8 +143,6 @@ struct Pipeline {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->copy_stream);
         for (Slot& s : slot) {
-            if (s.h_in) cudaFreeHost(s.h_in);
-            if (s.h_out) cudaFreeHost(s.h_out);
             if (s.d_in) cudaFreeAsync(s.d_in, ctx->stream);
             if (s.d_seg) cudaFreeAsync(s.d_seg, ctx->stream);
             if (s.k_done) cudaEventDestroy(s.k_done);
@@ -162,9 +160,27 @@ struct Pipeline {
         CU_TRY(ctx, cudaSetDevice(ctx->device));
         cells0 = ctx->next_cell + kSlots + 1 <= kRingCells ? ctx->next_cell : 0;
         ctx->next_cell = (cells0 + kSlots + 1) % kRingCells;
+        static_assert(kSlots == 3, "the context caches three ring slots");
+        if (ctx->stream_chunk != chunk || ctx->stream_out_cap != out_cap) {   // (re)build the context's pinned rings
+            for (int i = 0; i < kSlots; ++i) {
+                if (ctx->h_stream_in[i]) cudaFreeHost(ctx->h_stream_in[i]);
+                if (ctx->h_stream_out[i]) cudaFreeHost(ctx->h_stream_out[i]);
+                ctx->h_stream_in[i] = nullptr;
+                ctx->h_stream_out[i] = nullptr;
+            }
+            ctx->stream_chunk = ctx->stream_out_cap = 0;
+            for (int i = 0; i < kSlots; ++i) {
+                CU_TRY(ctx, cudaHostAlloc((void**)&ctx->h_stream_in[i], chunk, cudaHostAllocDefault));
+                CU_TRY(ctx, cudaHostAlloc((void**)&ctx->h_stream_out[i], out_cap * sizeof(uint64_t), cudaHostAllocDefault));
+            }
+            ctx->stream_chunk = chunk;
+            ctx->stream_out_cap = out_cap;
+        }
+        int si = 0;
         for (Slot& s : slot) {
-            CU_TRY(ctx, cudaHostAlloc((void**)&s.h_in, chunk, cudaHostAllocDefault));
-            CU_TRY(ctx, cudaHostAlloc((void**)&s.h_out, out_cap * sizeof(uint64_t), cudaHostAllocDefault));
+            s.h_in = ctx->h_stream_in[si];
+            s.h_out = ctx->h_stream_out[si];
+            ++si;
             CU_TRY(ctx, cudaMallocAsync((void**)&s.d_in, chunk + 16, ctx->stream));
             CU_TRY(ctx, cudaMallocAsync((void**)&s.d_seg, (chunk + 2) * sizeof(uint64_t), ctx->stream));
             CU_TRY(ctx, cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));

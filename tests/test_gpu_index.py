@@ -829,3 +829,31 @@ def test_shard_build_to_host_pipeline(ctx):
     full = np.concatenate(got)
     assert redone == [False, True]
     assert full.shape == want2.shape and (full == want2).all()
+
+
+def test_beyond_4gib_positions(ctx):
+    """Maximum-size edge: an input just past 2^32 bytes in ONE launch (positions need more than 32 bits, the
+    reference's u32 arithmetic in seek_* would wrap: SURVEY 8c quirk vi).  Count, wrapping sum and the entries
+    around the 2^32 boundary against the oracle; K5 over the whole tape."""
+    import torch
+    target = (1 << 32) + (64 << 20)
+    data, rows = gen.unquoted(target, seed=51, nfields=256, modulus=10 ** 15)   # wide rows keep E < 2^32
+    n = data.size
+    dev = torch.device("cuda", ctx.device)
+    d = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+    d[:n].copy_(torch.from_numpy(data))
+    idx = ctx.index_build_device(d.data_ptr(), n)
+    E = len(idx)
+    cnt, checksum = O.read_sse_timed(O.aligned_copy(data))
+    assert E == cnt == 1 + 256 * (rows + 1)
+    host = idx.to_host()
+    assert int(host.sum(dtype=np.uint64)) == checksum
+    assert int(host[-1]) == n - 1 and int(host[-1]) > (1 << 32)
+    assert (np.diff(host[1:].view(np.int64)) > 0).all()
+    k = int(np.searchsorted(host, np.uint64(1 << 32)))
+    lo = max(k - 2000, 1)
+    win = data[int(host[lo]):int(host[k + 2000]) + 1]
+    want = O.closed_form_numpy(win, 0, int(host[lo]), with_sentinel=False)
+    assert (host[lo:k + 2001] == want).all()
+    assert idx.tape_validate(256, False)["ok"] == 1
+    idx.free()
