@@ -332,6 +332,17 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     e2e_gbs = total_bytes / e2e_s / 1e9
     assert ln == E_local, (ln, E_local)
 
+    # the same call on ordinary (pageable) memory, as a caller holding an mmap and a Vec would make it: informational
+    e2e_pageable = None
+    if world == 1:
+        out_pg = np.empty(E_local + 1024, dtype=np.uint64)
+        out_pg[::512] = 0
+        ctx.index_build_to_host(data.ctypes.data, n, out_pg.ctypes.data, out_pg.size)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.index_build_to_host(data.ctypes.data, n, out_pg.ctypes.data, out_pg.size)
+        e2e_pageable = n / ((time.perf_counter() - t0) / 3) / 1e9
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's CPU path on this box's host cores ----
@@ -361,7 +372,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "csv_gbs_kernel_only": n / (k_ms * 1e-3) / 1e9},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_gbs, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8 * E_local,
-                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "pageable_buffers_gbs": e2e_pageable,
                     "api": "csvb200_index_build_to_host" if world == 1 else
                            "csvb200_shard_build_to_host + all_gather + csvb200_shard_job_verify (csv_simd_b200.dist.sharded_index_build_to_host)"},
             "gpu_launches": launches,

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "slice_pool.h"
 
 using namespace csvb200;
 
@@ -22,6 +23,12 @@ int fail(csvb200_ctx* ctx, int code, const std::string& msg)
 {
     if (ctx) ctx->err = msg;
     return code;
+}
+
+SlicePool& io_pool(csvb200_ctx* ctx)
+{
+    if (!ctx->pool) ctx->pool = new SlicePool(default_io_threads());
+    return *ctx->pool;
 }
 
 bool is_pinned(const void* p)
@@ -223,7 +230,7 @@ int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n)
     while (off < n) {
         const size_t len = std::min(kStageBytes, n - off);
         CU_TRY(ctx, cudaEventSynchronize(ctx->stage_free[b]));
-        std::memcpy(ctx->h_stage[b], h_src + off, len);
+        parallel_memcpy(io_pool(ctx), ctx->h_stage[b], h_src + off, len);   // one thread cannot feed PCIe
         CU_TRY(ctx, cudaMemcpyAsync(d_dst + off, ctx->h_stage[b], len, cudaMemcpyHostToDevice, ctx->stream));
         CU_TRY(ctx, cudaEventRecord(ctx->stage_free[b], ctx->stream));
         off += len;
@@ -313,6 +320,11 @@ void csvb200_ctx_destroy(csvb200_ctx* ctx)
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_cells) cudaFree(ctx->d_cells);
     if (ctx->h_cells) cudaFreeHost(ctx->h_cells);
+    delete ctx->pool;
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_bounce[i]) cudaFreeHost(ctx->h_bounce[i]);
+        if (ctx->bounce_done[i]) cudaEventDestroy(ctx->bounce_done[i]);
+    }
     if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
     for (int i = 0; i < 3; ++i) {
         if (ctx->h_stream_in[i]) cudaFreeHost(ctx->h_stream_in[i]);
@@ -600,6 +612,28 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
         }
     }
     // ---- as each chunk's kernel finishes, send its index segment down on the second stream ----
+    // A pinned destination is DMA'd in place.  A pageable one (a plain Vec<usize>) would make every copy a
+    // synchronous driver-staged transfer, so its segments come down into two pinned bounce buffers and the
+    // context's host threads move them on while the next piece is in flight.
+    const bool bounce = dst != nullptr && !is_pinned(dst);
+    if (bounce) {
+        for (int i = 0; i < 2 && rc == CSVB200_OK; ++i) {
+            cudaError_t e = cudaSuccess;
+            if (!ctx->h_bounce[i]) e = cudaHostAlloc((void**)&ctx->h_bounce[i], kBounceEntries * sizeof(uint64_t), cudaHostAllocDefault);
+            if (e == cudaSuccess && !ctx->bounce_done[i]) e = cudaEventCreateWithFlags(&ctx->bounce_done[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                rc = fail(ctx, CSVB200_ERR_OOM, std::string("bounce buffers: ") + cudaGetErrorString(e));
+            }
+        }
+    }
+    size_t piece_pos[2] = {0, 0}, piece_len[2] = {0, 0}, pieces = 0, flushed = 0;
+    auto flush_piece = [&](size_t k) -> cudaError_t {   // piece k (in order): wait for its D2H, copy it to dst
+        const int b = (int)(k & 1);
+        cudaError_t e = cudaEventSynchronize(ctx->bounce_done[b]);
+        if (e == cudaSuccess) parallel_memcpy(io_pool(ctx), dst + piece_pos[b], ctx->h_bounce[b], piece_len[b] * sizeof(uint64_t));
+        return e;
+    };
     size_t copied = 0;  // entries already on their way to dst (including the sentinel)
     bool overflow = false, dst_small = false;
     for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
@@ -610,9 +644,25 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
             if (upto > dst_cap || (upto && !dst)) dst_small = true;
             if (!overflow && !dst_small && upto > copied) {
                 e = cudaStreamWaitEvent(s_down, done[c], 0);
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(dst + copied, d_index + copied, (upto - copied) * sizeof(uint64_t),
-                                        cudaMemcpyDeviceToHost, s_down);
+                if (!bounce) {
+                    if (e == cudaSuccess)
+                        e = cudaMemcpyAsync(dst + copied, d_index + copied, (upto - copied) * sizeof(uint64_t),
+                                            cudaMemcpyDeviceToHost, s_down);
+                } else {
+                    for (size_t pos = copied; pos < upto && e == cudaSuccess; pos += kBounceEntries) {
+                        const size_t len = std::min(kBounceEntries, upto - pos);
+                        const int b = (int)(pieces & 1);
+                        if (pieces >= 2) {   // the buffer still holds piece (pieces - 2): move it on first
+                            e = flush_piece(flushed++);
+                            if (e != cudaSuccess) break;
+                        }
+                        e = cudaMemcpyAsync(ctx->h_bounce[b], d_index + pos, len * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_down);
+                        if (e == cudaSuccess) e = cudaEventRecord(ctx->bounce_done[b], s_down);
+                        piece_pos[b] = pos;
+                        piece_len[b] = len;
+                        ++pieces;
+                    }
+                }
                 copied = upto;
             }
             if (c + 1 == nchunks) *len_out = upto;
@@ -620,6 +670,12 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
         if (e != cudaSuccess) {
             cudaGetLastError();
             rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
+        }
+    }
+    while (rc == CSVB200_OK && flushed < pieces) {
+        if (flush_piece(flushed++) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(ctx, CSVB200_ERR_CUDA, "e2e pipeline: bounce copy failed");
         }
     }
     if (rc == CSVB200_OK) {
@@ -1052,7 +1108,12 @@ static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fl
     SEEK_TRY(cudaMemsetAsync(d_oob, 0, sizeof(uint32_t), s_up));
     if (!direct) {
         if (ctx->seek_stage_bytes < nslots * slot_bytes) {   // page-locking is slow: keep the buffer in the context
-            if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
+            delete ctx->pool;
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_bounce[i]) cudaFreeHost(ctx->h_bounce[i]);
+        if (ctx->bounce_done[i]) cudaEventDestroy(ctx->bounce_done[i]);
+    }
+    if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
     for (int i = 0; i < 3; ++i) {
         if (ctx->h_stream_in[i]) cudaFreeHost(ctx->h_stream_in[i]);
         if (ctx->h_stream_out[i]) cudaFreeHost(ctx->h_stream_out[i]);

@@ -9,6 +9,10 @@
 #include "internal.h"
 
 namespace csvb200 {
+class SlicePool;
+}
+
+namespace csvb200 {
 constexpr size_t kCells = 4096;              // result cells (4 x u64 each): a ring of kRingCells + one scratch cell
 constexpr size_t kCellWords = 4;
 constexpr size_t kRingCells = kCells - 1;    // the last cell is the out-of-bounds flag of the async seek calls
@@ -16,6 +20,7 @@ constexpr uint64_t kDefaultPredictWindow = 64u << 10;
 constexpr size_t kStageBytes = 32u << 20;    // pinned staging buffers for pageable input
 constexpr int kStageBufs = 2;
 constexpr size_t kE2eChunk = 64u << 20;      // H2D / kernel / D2H pipeline granularity
+constexpr size_t kBounceEntries = 4u << 20;  // 32 MiB per bounce buffer
 }  // namespace csvb200
 
 struct csvb200_ctx {
@@ -34,6 +39,9 @@ struct csvb200_ctx {
     uint8_t* h_stream_in[3] = {nullptr, nullptr, nullptr};
     uint64_t* h_stream_out[3] = {nullptr, nullptr, nullptr};
     size_t stream_chunk = 0, stream_out_cap = 0;
+    uint64_t* h_bounce[2] = {nullptr, nullptr};   // pinned bounce buffers for index segments headed to pageable memory
+    cudaEvent_t bounce_done[2] = {nullptr, nullptr};
+    csvb200::SlicePool* pool = nullptr;   // host threads for pread / staging copies, created on first use (io_pool)
     uint8_t* h_seek_stage = nullptr;   // pinned staging of the batched seeks from pageable arrays (kept across calls)
     size_t seek_stage_bytes = 0;
     uint8_t* h_stage[csvb200::kStageBufs] = {nullptr, nullptr};
@@ -81,6 +89,7 @@ namespace csvb200 {
 int fail(csvb200_ctx* ctx, int code, const std::string& msg);
 int ensure_scratch(csvb200_ctx* ctx, size_t bytes);
 bool is_pinned(const void* p);
+SlicePool& io_pool(csvb200_ctx* ctx);   // the context's host-thread pool (CSVB200_IO_THREADS)
 // host -> device copy of n bytes on the context's stream; pinned sources go straight to cudaMemcpyAsync,
 // pageable ones through the context's pinned staging ring
 int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n);
