@@ -73,8 +73,8 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
     if (num_tiles > 0xffffffffull) return fail(ctx, CSVB200_ERR_INVALID_ARG, "input too large for one launch");
     uint64_t* d_cell = ctx->d_cells + idx->cell * kCellWords;
     uint64_t* h_cell = ctx->h_cells + idx->cell * kCellWords;
-    if (idx->out_base == 1 && idx->cap > 0) CU_TRY(ctx, cudaMemsetAsync(idx->d_index, 0, 8, ctx->stream));  // sentinel
     if (num_tiles == 0) {
+        if (idx->out_base == 1 && idx->cap > 0) CU_TRY(ctx, cudaMemsetAsync(idx->d_index, 0, 8, ctx->stream));  // sentinel alone
         h_cell[0] = 0;
         h_cell[1] = idx->carry_parity;
     } else {
@@ -96,6 +96,8 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
         p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
         p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
         p.result = d_cell;
+        p.result_host = ctx->host_result ? h_cell : nullptr;
+        p.write_sentinel = idx->out_base == 1 ? 1u : 0u;
         p.result2 = idx->d_result2;
         p.result2_words = 2;
         p.shard_par = idx->d_shard_par;
@@ -128,7 +130,8 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             CU_TRY(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
             ctx->timed = true;
         }
-        CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (!ctx->host_result)
+            CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU_TRY(ctx, cudaEventRecord(idx->done, ctx->stream));
     idx->synced = false;
@@ -280,6 +283,7 @@ int csvb200_ctx_create(int device, csvb200_ctx** out)
         if (std::strcmp(k, "tma") == 0) ctx->kernel_override = 2;
     }
     if (const char* t = std::getenv("CSVB200_TUNE")) ctx->tune = (uint32_t)std::atoi(t);
+    if (const char* t = std::getenv("CSVB200_HOST_RESULT")) ctx->host_result = std::atoi(t) != 0;
     if (const char* t = std::getenv("CSVB200_E2E_CHUNK_MB")) {
         const long mb = std::atol(t);
         if (mb >= 1 && mb <= 4096) ctx->e2e_chunk = (size_t)mb << 20;
@@ -297,7 +301,7 @@ int csvb200_ctx_create(int device, csvb200_ctx** out)
     if ((e = cudaEventCreate(&ctx->ev_k0)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&ctx->ev_k1)) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc((void**)&ctx->d_cells, kCells * kCellWords * sizeof(uint64_t))) != cudaSuccess) return bail(e);
-    if ((e = cudaHostAlloc((void**)&ctx->h_cells, kCells * kCellWords * sizeof(uint64_t), cudaHostAllocDefault)) !=
+    if ((e = cudaHostAlloc((void**)&ctx->h_cells, kCells * kCellWords * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable)) !=
         cudaSuccess)
         return bail(e);
     // keep freed blocks in the stream-ordered pool so per-build allocations are reused, not re-mapped
@@ -534,7 +538,6 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
     const uint64_t out_base = o.emit_sentinel ? 1 : 0;
     if (!d_bytes) CU_TRY(ctx, cudaMallocAsync((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, s_up));
     CU_TRY(ctx, cudaMallocAsync((void**)&d_index, cap * sizeof(uint64_t), s_up));
-    if (out_base) CU_TRY(ctx, cudaMemsetAsync(d_index, 0, sizeof(uint64_t), s_up));  // sentinel (src/reader.rs:216)
     // cells: cell0 = carry into chunk 0; cell[c+1] = result of chunk c
     const size_t cell0 = ctx->next_cell + nchunks + 1 <= kRingCells ? ctx->next_cell : 0;
     ctx->next_cell = (cell0 + nchunks + 1) % kRingCells;
@@ -584,6 +587,8 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
         p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
         p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
         p.result = d_cells + (c + 1) * kCellWords;
+        p.result_host = ctx->host_result ? h_cells + (c + 1) * kCellWords : nullptr;
+        p.write_sentinel = (c == 0 && out_base) ? 1u : 0u;
         p.result2_words = 2;
         if (o.d_result4) p.total_out = reinterpret_cast<unsigned long long*>(o.d_result4 + 3);
         p.tune = ctx->tune;
@@ -591,7 +596,7 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
         if (ctx->kernel_override == 1) use_tma = false;
         if (e == cudaSuccess) e = use_tma ? launch_index_build_tma(p, s_up) : launch_index_build(p, s_up);
         ctx->launches += 1;
-        if (e == cudaSuccess)
+        if (e == cudaSuccess && !ctx->host_result)
             e = cudaMemcpyAsync(h_cells + (c + 1) * kCellWords, d_cells + (c + 1) * kCellWords, 2 * sizeof(uint64_t),
                                 cudaMemcpyDeviceToHost, s_up);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming);
@@ -1108,16 +1113,7 @@ static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fl
     SEEK_TRY(cudaMemsetAsync(d_oob, 0, sizeof(uint32_t), s_up));
     if (!direct) {
         if (ctx->seek_stage_bytes < nslots * slot_bytes) {   // page-locking is slow: keep the buffer in the context
-            delete ctx->pool;
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->h_bounce[i]) cudaFreeHost(ctx->h_bounce[i]);
-        if (ctx->bounce_done[i]) cudaEventDestroy(ctx->bounce_done[i]);
-    }
-    if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
-    for (int i = 0; i < 3; ++i) {
-        if (ctx->h_stream_in[i]) cudaFreeHost(ctx->h_stream_in[i]);
-        if (ctx->h_stream_out[i]) cudaFreeHost(ctx->h_stream_out[i]);
-    }
+            if (ctx->h_seek_stage) cudaFreeHost(ctx->h_seek_stage);
             ctx->h_seek_stage = nullptr;
             ctx->seek_stage_bytes = 0;
             SEEK_TRY(cudaHostAlloc((void**)&ctx->h_seek_stage, nslots * slot_bytes, cudaHostAllocDefault));

@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
             if (tile == p.num_tiles - 1) {
                 write_result(p, cend, pend);
             }
+            if (tile == 0u && p.write_sentinel && p.cap > 0) p.index[0] = 0ull;
             if (p.total_out != nullptr && (o0 | o1) != 0u) atomicAdd(p.total_out, (unsigned long long)(o0 + o1));
         }
     }

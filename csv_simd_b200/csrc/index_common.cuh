@@ -60,6 +60,10 @@ __device__ __forceinline__ void write_result(const BuildParams& p, uint64_t cend
 {
     p.result[0] = cend;
     p.result[1] = pend;
+    if (p.result_host != nullptr) {
+        p.result_host[0] = cend;
+        p.result_host[1] = pend;
+    }
     if (p.result2 != nullptr) {
         p.result2[0] = cend;
         p.result2[1] = pend;

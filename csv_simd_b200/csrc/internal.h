@@ -44,6 +44,8 @@ struct BuildParams {
     uint64_t* desc;          // [num_tiles] look-back descriptors, zeroed before launch
     uint32_t* ticket;        // dynamic tile counter, zeroed before launch
     uint64_t* result;        // {entries emitted through the end of this launch, end parity}
+    uint64_t* result_host;   // optional pinned (UVA-mapped) host mirror of `result`: written straight over PCIe, no D2H copy node
+    uint32_t write_sentinel; // the CTA of tile 0 writes index[0] = 0 (src/reader.rs:216) instead of a separate memset
     uint64_t* result2;       // optional second copy of `result` in caller-owned device memory
     uint32_t result2_words;  // 2, or 4: {entries, end parity, carry parity used, (total separators via total_out)}
     // optional: every CTA adds the separator count (inside + outside quotes) of its tiles; zeroed by the

@@ -130,7 +130,6 @@ struct Pipeline {
         int rc = ensure_scratch(ctx, sbytes);
         if (rc) return rc;
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, st));
-        if (c == 0) CU_TRY(ctx, cudaMemsetAsync(s.d_seg, 0, sizeof(uint64_t), st));   // sentinel (src/reader.rs:216)
         BuildParams p{};
         p.in = s.d_in;
         p.n = s.bytes;
@@ -144,12 +143,15 @@ struct Pipeline {
         p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
         p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
         p.result = ctx->d_cells + s.cell * kCellWords;
+        p.result_host = ctx->host_result ? ctx->h_cells + s.cell * kCellWords : nullptr;
+        p.write_sentinel = c == 0 ? 1u : 0u;     // sentinel (src/reader.rs:216)
         p.result2_words = 2;
         p.tune = ctx->tune;
         CU_TRY(ctx, use_tma ? launch_index_build_tma(p, st) : launch_index_build(p, st));
         ctx->launches += 1;
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_cells + s.cell * kCellWords, ctx->d_cells + s.cell * kCellWords,
-                                    2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (!ctx->host_result)
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_cells + s.cell * kCellWords, ctx->d_cells + s.cell * kCellWords,
+                                        2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaEventRecord(s.k_done, st));
         s.busy = true;
         total_bytes += s.bytes;
