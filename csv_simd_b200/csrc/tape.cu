@@ -22,58 +22,59 @@ __device__ __forceinline__ uint64_t ldg_u64(const uint64_t* p)
     return v;
 }
 
-__device__ __forceinline__ bool slot_ok(const TapeValidateParams& p, uint64_t s, uint64_t k, uint64_t pos, uint32_t b,
-                                        bool in_range)
-{
-    if (!in_range) return false;
-    const uint64_t jump = p.jump;
-    if (p.crlf) {
-        if (k + 2 < jump) return b == 0x2Cu;
-        if (k + 2 == jump) return b == 0x0Du;
-        return b == 0x0Au && ldg_u64(p.index + s - 1) + 1 == pos;
-    }
-    return k + 1 < jump ? b == 0x2Cu : (b == 0x0Au || b == 0x0Du);
-}
-
+// One row of 32 slots per warp step.  Everything that does not depend on the slot is hoisted: CRLF / LF is a
+// template parameter, k = (s - 1) % jump lives in 32 bits and advances by 32 % jump, and the only 64-bit
+// work left per slot is the position arithmetic (the first version spent ~100 instructions per slot row on
+// 64-bit modulo / select chains and was issue-bound at 0.55 of the HBM peak).
+template <bool kCrlf>
 __global__ void __launch_bounds__(256) tape_validate_kernel(const TapeValidateParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t jump = p.jump;
+    const uint32_t jump = (uint32_t)p.jump;
+    const uint32_t nl0 = jump - (kCrlf ? 2u : 1u);    // first line-end slot of a row (k >= nl0 is CR / LF territory)
     const uint64_t last = p.index_len - 1;            // slots are 1 .. last; i = s - 1 in [0, last)
-    const uint32_t step = (uint32_t)(32ull % jump);   // k advances by 32 slots per warp row
-    uint64_t bad = UINT64_MAX;
-    // each warp owns runs of kRun consecutive slots: one modulo per run, then k += 32 (mod jump) per row.
-    // kUnroll rows are in flight together: the byte load depends on the index load, so the loop is
-    // latency-bound without them (0.62 -> measured again in profiles/).
+    const uint32_t step = 32u % jump;                 // k advances by 32 slots per warp row
+    const uint64_t* __restrict__ index = p.index + 1; // index[i] here is slot s = i + 1
+    uint64_t bad = UINT64_MAX;                        // smallest failing i
     constexpr int kUnroll = 4;
     constexpr uint64_t kRun = 32 * 16;
     for (uint64_t run = warp0 * kRun; run < last; run += warps * kRun) {
         const uint64_t run_end = run + kRun < last ? run + kRun : last;
-        uint64_t k = (run + lane) % jump;             // slot s = 1 + run + lane  ->  k = (s - 1) % jump
+        uint32_t k = (uint32_t)((run + lane) % jump);
         for (uint64_t i = run + lane; i < run_end; i += 32 * kUnroll) {
-            uint64_t pos[kUnroll], kk[kUnroll];
-            uint32_t byte[kUnroll];
-            bool live[kUnroll], inr[kUnroll];
+            uint64_t pos[kUnroll];
+            uint32_t byte[kUnroll], kk[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                live[u] = i + 32ull * u < run_end;
-                pos[u] = live[u] ? ldg_u64(p.index + i + 32ull * u + 1) : 0ull;
+                const uint64_t iu = i + 32ull * u;
+                pos[u] = iu < run_end ? ldg_u64(index + iu) : UINT64_MAX;   // UINT64_MAX - bias >= n: treated as skipped below
                 kk[u] = k;
                 k += step;
-                if (k >= jump) k -= jump;
+                k = k >= jump ? k - jump : k;
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const uint64_t rel = pos[u] - p.pos_bias;
-                inr[u] = rel < p.n;
-                byte[u] = live[u] && inr[u] ? p.bytes[rel] : 0u;
+                byte[u] = rel < p.n ? (uint32_t)p.bytes[rel] : 0x100u;      // 0x100: no separator there (out of range)
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const uint64_t s = i + 32ull * u + 1;
-                if (live[u] && !slot_ok(p, s, kk[u], pos[u], byte[u], inr[u]) && s < bad) bad = s;
+                const uint64_t iu = i + 32ull * u;
+                if (iu >= run_end) continue;
+                const uint32_t b = byte[u];
+                bool ok;
+                if (kk[u] < nl0) {
+                    ok = b == 0x2Cu;
+                } else if (!kCrlf) {
+                    ok = b == 0x0Au || b == 0x0Du;
+                } else if (kk[u] == nl0) {
+                    ok = b == 0x0Du;
+                } else {
+                    ok = b == 0x0Au && ldg_u64(index + iu - 1) + 1 == pos[u];   // the LF directly after its CR
+                }
+                if (!ok && iu < bad) bad = iu;
             }
         }
     }
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(256) tape_validate_kernel(const TapeValidatePa
         const uint64_t o = __shfl_xor_sync(0xffffffffu, bad, d);
         bad = o < bad ? o : bad;
     }
-    if (lane == 0 && bad != UINT64_MAX) atomicMin(reinterpret_cast<unsigned long long*>(p.first_bad_slot), (unsigned long long)bad);
+    if (lane == 0 && bad != UINT64_MAX)
+        atomicMin(reinterpret_cast<unsigned long long*>(p.first_bad_slot), (unsigned long long)(bad + 1));
 }
 
 __global__ void gather_slots_kernel(const uint64_t* __restrict__ index, uint64_t index_len,
@@ -113,7 +115,11 @@ cudaError_t launch_tape_validate(const TapeValidateParams& p, cudaStream_t strea
     const uint64_t max_blocks = (uint64_t)sms * 8;
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks == 0) blocks = 1;
-    tape_validate_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+    if (p.jump > 0xffffffffull) return cudaErrorInvalidValue;
+    if (p.crlf)
+        tape_validate_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    else
+        tape_validate_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
