@@ -109,6 +109,9 @@ __device__ __forceinline__ void copy_out_range(const BuildParams& p, const uint1
     uint64_t* out = p.index + gbase;
     if (gbase + j1 <= p.cap) {
         const uint32_t j1e = j1 & ~1u;
+        // (Splitting tile_pos into a shared high word and one 32-bit add per entry halves this loop's instructions
+        //  (11 -> 5 per store) and measured SLOWER twice, 0.416 vs 0.400 ms: the stores then leave in bursts that
+        //  collide with the TMA reads; the paced version interleaves better with them.)
         for (uint32_t j = j0 + 2u * tid; j < j1e; j += 2u * kThreads) {
             const uint32_t pr = *reinterpret_cast<const uint32_t*>(&stg[j - local0]);
             stg_128(out + j, tile_pos + (pr & 0xffffu), tile_pos + (pr >> 16));
@@ -159,7 +162,8 @@ __device__ __forceinline__ void compact_sub(SmemTma& sm, const BuildParams& p, c
                 const uint32_t rel0 = tid * kBytesPerThread + 32u * g;
                 const uint32_t c = (uint32_t)__popc(m);
                 // two entries per trip: immediate store offsets, one pointer bump, half the branches
-                // (0.396 vs 0.403 ms on cfg2 against the one-entry loop kept below for A/B: CSVB200_TUNE=64)
+                // (0.396 vs 0.403 ms on cfg2 against the one-entry loop kept below for A/B: CSVB200_TUNE=64;
+                //  walking two groups per loop for more ILP measured slower, 0.439 ms: this phase is issue-bound)
 #pragma unroll 1
                 for (uint32_t k = 0; k + 1u < c; k += 2u) {
                     const uint32_t b0 = (uint32_t)__ffs((int)m) - 1u;
