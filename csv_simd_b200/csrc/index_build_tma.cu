@@ -490,7 +490,7 @@ cudaError_t launch_index_build_tma(const BuildParams& p_in, cudaStream_t stream)
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(p.in), gdim, gstride, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);   // (promotion NONE: no difference)
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     static int grid_cap = 0;
     if (grid_cap == 0) {

@@ -26,7 +26,8 @@ __device__ __forceinline__ uint4 ldg_stream_128(const void* p)
 }
 __device__ __forceinline__ void stg_128(void* p, uint64_t a, uint64_t b)
 {
-    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    // .cs: the index is written once and never read by this kernel (0.3979 vs 0.4006 ms on cfg2 against the plain store)
+    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
 struct WarpState {
