@@ -134,7 +134,7 @@ def ncu_traffic(workload: str, n: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the hot kernel, from the committed
     ncu --set full capture of the same 1 GiB workload (profiles/); None when no capture matches."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_v5_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_v6_traffic.json")) as f:
             t = json.load(f)
         key = "cfg2" if workload == "cfg2_unquoted" else "cfg3"
         if abs(n - GiB) > (1 << 20) or workload == "cfg4_sharded":
