@@ -142,7 +142,10 @@ __global__ void __launch_bounds__(kMatThreads) materialize_offsets_kernel(const 
 __global__ void __launch_bounds__(kMatThreads) materialize_write_kernel(const MaterializeParams p)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint8_t* x = p.bytes;
+    // restrict-qualified local copies: without them every byte load has to wait for the previous byte store
+    // (the compiler must assume out aliases bytes), which serialises the copy into load -> store round trips
+    const uint8_t* __restrict__ x = p.bytes;
+    uint8_t* __restrict__ out = p.out;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nrec; i += stride) {
         uint64_t a, b;
         if (!field_range(p, p.first_record + (uint32_t)i, a, b)) continue;
@@ -150,11 +153,19 @@ __global__ void __launch_bounds__(kMatThreads) materialize_write_kernel(const Ma
         const uint64_t o_end = p.offsets[i + 1];
         if (o_end > p.out_cap) continue;   // host form checks the capacity first; device form clips whole values
         if (!trim_and_test(p, a, b)) {
-            for (; a < b; ++a) p.out[o++] = x[a];
+            // eight bytes in flight per trip
+            for (; a + 8 <= b; a += 8, o += 8) {
+                uint8_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = x[a + k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out[o + k] = v[k];
+            }
+            for (; a < b; ++a) out[o++] = x[a];
         } else {
             while (a < b) {
-                if (x[a] == 0x22u && a + 1 < b && x[a + 1] == 0x22u) ++a;
-                p.out[o++] = x[a];
+                if (x[a] == 0x22u && a + 1 < b && x[a + 1] == 0x22u) ++a;   // "" -> "
+                out[o++] = x[a];
                 ++a;
             }
         }
