@@ -77,6 +77,7 @@ SIGNATURES = {
                                               C.c_void_p, C.c_size_t, szp, C.c_void_p, vpp]),
     "csvb200_shard_job_verify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, szp, C.POINTER(C.c_int)]),
     "csvb200_shard_job_free": (None, [C.c_void_p]),
+    "csvb200_index_wrap_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, vpp]),
     "csvb200_index_sync": (C.c_int, [C.c_void_p]),
     "csvb200_index_len": (C.c_size_t, [C.c_void_p]),
     "csvb200_index_end_parity": (C.c_int, [C.c_void_p]),

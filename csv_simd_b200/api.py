@@ -218,6 +218,13 @@ class Context:
         self._check(rc)
         return ln.value, bool(redone.value)
 
+    def index_wrap_device(self, d_entries: int, length: int, input_bytes: int, d_bytes: int = 0) -> "StructureIndex":
+        """csvb200_index_wrap_device: an index object over caller-owned device entries (not freed with it)."""
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_wrap_device(self._h, C.c_void_p(d_entries), length, input_bytes,
+                                                        C.c_void_p(d_bytes or 0), C.byref(h)))
+        return StructureIndex(self, h)
+
     # -- input validation / on-disk index ------------------------------------------------------
     def validate_utf8(self, data):
         """(valid_up_to or None when well-formed UTF-8, is_ascii) -- csvb200_validate_utf8."""

@@ -839,6 +839,24 @@ int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n
     return CSVB200_OK;
 }
 
+int csvb200_index_wrap_device(csvb200_ctx* ctx, const uint64_t* d_entries, size_t len, size_t input_bytes,
+                              const void* d_bytes, csvb200_index** out)
+{
+    if (!ctx || !out || !d_entries || len == 0) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument / empty index");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    csvb200_index* idx = nullptr;
+    int rc = new_index(ctx, &idx);
+    if (rc) return rc;
+    idx->d_index = const_cast<uint64_t*>(d_entries);
+    idx->borrowed = true;
+    idx->cap = idx->len = len;
+    idx->n = input_bytes;
+    idx->src = static_cast<const uint8_t*>(d_bytes);   // optional: enables tape_validate / materialize / gather
+    idx->synced = true;
+    *out = idx;
+    return CSVB200_OK;
+}
+
 int csvb200_index_sync(csvb200_index* idx)
 {
     if (!idx) return CSVB200_ERR_INVALID_ARG;
@@ -902,7 +920,7 @@ void csvb200_index_free(csvb200_index* idx)
     if (!idx) return;
     csvb200_ctx* ctx = idx->ctx;
     cudaSetDevice(ctx->device);
-    if (idx->d_index) cudaFreeAsync(idx->d_index, ctx->stream);
+    if (idx->d_index && !idx->borrowed) cudaFreeAsync(idx->d_index, ctx->stream);
     if (idx->d_bytes_owned) cudaFreeAsync(idx->d_bytes_owned, ctx->stream);
     if (idx->done) cudaEventDestroy(idx->done);
     cudaGetLastError();

@@ -78,6 +78,7 @@ struct csvb200_index {
     bool verified = false;
     size_t carry_cell = 0;
     uint8_t* d_bytes_owned = nullptr;
+    bool borrowed = false;                  // d_index belongs to the caller (csvb200_index_wrap_device): never freed here
     // Tape metadata (TapeCore::init)
     bool tape_ready = false;
     uint32_t field_cnt = 0, record_cnt = 0;

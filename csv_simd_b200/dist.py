@@ -92,6 +92,7 @@ class ShardedIndex:
     total_len: int              # length of the whole (distributed) index, sentinel included
     carry_in: int               # quote parity entering this shard
     parities: List[int]
+    counts: object = None       # resolved: entries per rank (rank 0 incl. the sentinel); resolve=False: the device tensor
 
 
 def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: int, group=None,
@@ -133,7 +134,7 @@ def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: i
         carries = [int(c) for c in host[1:2 * world:2]]
         g = host[2 * world:]
         ps = [(int(g[4 * k + 1]) ^ int(g[4 * k + 2])) & 1 for k in range(world)]  # shard parity = end ^ carry used
-        return ShardedIndex(idx, exclusive_bases(counts)[rank], sum(counts), carries[rank], ps)
+        return ShardedIndex(idx, exclusive_bases(counts)[rank], sum(counts), carries[rank], ps, counts)
     par_local = torch.empty(1, dtype=torch.int32, device=device)
     ctx.shard_quote_parity_device(dev_ptr, n, par_local.data_ptr())              # pass A
     pars = torch.empty(world, dtype=torch.int32, device=device)
@@ -152,7 +153,7 @@ def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: i
     counts = [int(c) for c in host[0::2]]
     counts[0] += 1                                                              # sentinel lives on rank 0
     ps = [int(v) for v in pars.cpu().tolist()]
-    return ShardedIndex(idx, exclusive_bases(counts)[rank], sum(counts), carry_in_parities(ps)[rank], ps)
+    return ShardedIndex(idx, exclusive_bases(counts)[rank], sum(counts), carry_in_parities(ps)[rank], ps, counts)
 
 
 def sharded_index_build_to_host(ctx: api.Context, host_ptr: int, n: int, global_offset: int, dst_ptr: int, dst_cap: int,
@@ -173,3 +174,53 @@ def sharded_index_build_to_host(ctx: api.Context, host_ptr: int, n: int, global_
     counts = [int(c) for c in final.cpu().tolist()[0::2]]
     counts[0] += 1
     return ln, exclusive_bases(counts)[rank], sum(counts), redone
+
+
+def segment_layout(counts: Sequence[int]):
+    """(bases, total) of the per-rank index segments; counts[0] includes the sentinel."""
+    bases = exclusive_bases(counts)
+    return bases, int(sum(int(c) for c in counts))
+
+
+def gather_segments(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """All ranks' index segments concatenated in rank order, on every rank: ONE all_gather of the segments padded
+    to the longest, then a local compaction.  `local` holds this rank's counts[rank] entries (int64 view of the
+    u64 positions); works on any backend (NCCL over NVLink on the GPUs, gloo in the CPU tests)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    counts = [int(c) for c in counts]
+    bases, total = segment_layout(counts)
+    width = max(max(counts), 1)
+    padded = torch.zeros(width, dtype=torch.int64, device=local.device)
+    padded[:counts[rank]] = local[:counts[rank]]
+    gathered = torch.empty(world * width, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    full = torch.empty(max(total, 1), dtype=torch.int64, device=local.device)
+    for k in range(world):
+        if counts[k]:
+            full[bases[k]:bases[k] + counts[k]] = gathered[k * width:k * width + counts[k]]
+    return full[:total] if total else full[:0]
+
+
+def replicate_index(ctx: api.Context, sharded: ShardedIndex, counts: Sequence[int], input_bytes: int, group=None):
+    """Every rank ends up with the WHOLE index ("segments are all-gathered if a replicated index is
+    wanted") as an index object the batched lookups (K4) run on locally: gather_segments + csvb200_index_wrap_device.
+    counts = entries per rank, rank 0 including the sentinel (ShardedIndex.counts).  Returns the StructureIndex; the
+    gathered tensor that owns its memory rides along as ._keepalive."""
+    device = torch.device("cuda", ctx.device)
+    rank = dist.get_rank(group)
+    seg = _segment_tensor(sharded.local, int(counts[rank]), device)
+    full = gather_segments(seg, counts, group)
+    idx = ctx.index_wrap_device(full.data_ptr(), int(full.numel()), input_bytes)
+    idx._keepalive = full
+    return idx
+
+
+def _segment_tensor(local_index, n_local: int, device) -> torch.Tensor:
+    """This rank's segment as a torch view of the library's device memory (zero copy)."""
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (max(n_local, 1),), "typestr": "<i8",
+                                    "data": (local_index.device_ptr, False), "version": 2}
+    if n_local == 0:
+        return torch.zeros(0, dtype=torch.int64, device=device)
+    return torch.as_tensor(_Raw(), device=device)[:n_local]

@@ -185,6 +185,12 @@ int csvb200_shard_job_verify(csvb200_shard_job* job, const uint64_t* d_gathered,
 void csvb200_shard_job_free(csvb200_shard_job* job);
 
 /* ---- index object: StructureIndex (src/stage1.rs:61) --------------------------------------- */
+/* Wrap `len` entries that already sit in device memory (e.g. the segments of a sharded build gathered
+ * into one array) as an index object, so the Tape / seek / validate / materialise calls run on them.
+ * The memory stays the caller's (never freed by csvb200_index_free) and must outlive the object;
+ * d_bytes (optional) is the device copy of the input the positions refer to. */
+int csvb200_index_wrap_device(csvb200_ctx* ctx, const uint64_t* d_entries, size_t len, size_t input_bytes,
+                              const void* d_bytes, csvb200_index** out);
 int csvb200_index_sync(csvb200_index* idx);
 size_t csvb200_index_len(csvb200_index* idx);          /* entries incl. the sentinel if emitted */
 int csvb200_index_end_parity(csvb200_index* idx);      /* quote parity after the last byte */

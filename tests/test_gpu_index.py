@@ -857,3 +857,31 @@ def test_beyond_4gib_positions(ctx):
     assert (host[lo:k + 2001] == want).all()
     assert idx.tape_validate(256, False)["ok"] == 1
     idx.free()
+
+
+def test_index_wrap_device(ctx):
+    """csvb200_index_wrap_device: caller-owned device entries behave like a built index (Tape, seeks, K5, K6)."""
+    import torch
+    raw = golden_bytes("sample_rx.csv")
+    dev = torch.device("cuda", ctx.device)
+    built = ctx.index_build(raw, cs.BUILD_KEEP_BYTES)
+    host = built.to_host()
+    entries = torch.from_numpy(host.view(np.int64).copy()).to(dev)
+    d_bytes = torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()).to(dev)
+    w = ctx.index_wrap_device(entries.data_ptr(), entries.numel(), len(raw), d_bytes.data_ptr())
+    assert len(w) == host.size and (w.to_host() == host).all()
+    assert w.tape_init(8, True) == built.tape_init(8, True)
+    for r, f in ((1, 2), (6, 3), (6, 8), (10, 1), (0, 0)):
+        assert w.seek_field(r, f) == built.seek_field(r, f)
+    assert w.seek_record(6) == built.seek_record(6)
+    assert w.tape_validate(8, True) == built.tape_validate(8, True)
+    a, b = w.materialize_column(2, 0, 7, 3), built.materialize_column(2, 0, 7, 3)
+    assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
+    w.free()                                   # must not free the caller's tensor
+    assert (entries.cpu().numpy().view(np.uint64) == host).all()
+    w2 = ctx.index_wrap_device(entries.data_ptr(), entries.numel(), len(raw))     # without the bytes
+    w2.tape_init(8, True)
+    with pytest.raises(cs.InvalidState):
+        w2.tape_validate(8, True)
+    w2.free()
+    built.free()

@@ -144,6 +144,11 @@ def _gloo_worker(rank, world, port, q):
         seg2 = O.closed_form_numpy(shard, carries[rank], lo, with_sentinel=(rank == 0))
         ok = ok and carries[rank] == carry and counts[rank] + (rank == 0) == seg2.size and (seg2 == seg).all()
         ok = ok and redo[rank] == (carry != 0) and 1 + sum(counts) == full.size
+        # replicated index: gather_segments puts the whole index on every rank (gloo stands in for NCCL)
+        seg_t = torch.from_numpy(seg.view(np.int64).copy())
+        cnts = [counts[0] + 1, counts[1]]
+        full_t = csd.gather_segments(seg_t, cnts)
+        ok = ok and full_t.numel() == full.size and (full_t.numpy().view(np.uint64) == full).all()
         q.put((rank, bool(ok), carry))
     finally:
         dist.destroy_process_group()
