@@ -843,6 +843,8 @@ int csvb200_index_wrap_device(csvb200_ctx* ctx, const uint64_t* d_entries, size_
                               const void* d_bytes, csvb200_index** out)
 {
     if (!ctx || !out || !d_entries || len == 0) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument / empty index");
+    if ((reinterpret_cast<uintptr_t>(d_bytes) & 15u) != 0 || (reinterpret_cast<uintptr_t>(d_entries) & 7u) != 0)
+        return fail(ctx, CSVB200_ERR_INVALID_ARG, "device input must be 16-byte aligned, entries 8-byte aligned");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     csvb200_index* idx = nullptr;
     int rc = new_index(ctx, &idx);
