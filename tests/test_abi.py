@@ -62,3 +62,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower().replace("no cpu fallback", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_links():
+    """include/csvb200.h is the drop-in boundary: it must compile as C99 (not just C++), and a C program that
+    references every declared function must link against libcsvb200.so (no compute call is made)."""
+    import subprocess
+    import tempfile
+    so = cbuild.build()
+    names = declared_symbols()
+    src = '#include "csvb200.h"\n#include <stdio.h>\nint main(void) {\n    const void* fns[] = {\n'
+    src += "".join(f"        (const void*)&{n},\n" for n in names)
+    src += ('    };\n    printf("%d %s %u\\n", csvb200_version(), csvb200_status_string(CSVB200_ERR_INVALID_CSV_FORMAT),'
+            ' (unsigned)(sizeof(fns) / sizeof(fns[0])));\n    return 0;\n}\n')
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-Wno-pedantic",
+                               "-I", os.path.join(ROOT, "include"), c, "-o", exe, "-L", os.path.dirname(so), "-lcsvb200",
+                               "-Wl,-rpath," + os.path.dirname(so)])
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        v, *msg, cnt = out.stdout.split()
+        assert int(v) == 100 and int(cnt) == len(names) and "Unsupported" in out.stdout
