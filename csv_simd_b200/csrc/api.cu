@@ -284,6 +284,7 @@ int csvb200_ctx_create(int device, csvb200_ctx** out)
     }
     if (const char* t = std::getenv("CSVB200_TUNE")) ctx->tune = (uint32_t)std::atoi(t);
     if (const char* t = std::getenv("CSVB200_HOST_RESULT")) ctx->host_result = std::atoi(t) != 0;
+    if (const char* t = std::getenv("CSVB200_E2E_RAMP")) ctx->e2e_ramp = std::atoi(t) != 0;
     if (const char* t = std::getenv("CSVB200_E2E_CHUNK_MB")) {
         const long mb = std::atol(t);
         if (mb >= 1 && mb <= 4096) ctx->e2e_chunk = (size_t)mb << 20;
@@ -527,8 +528,23 @@ struct PipeOpts {
 int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap, size_t* len_out,
                      const PipeOpts& o, bool* overflow_out, bool* dst_small_out = nullptr)
 {
-    const size_t chunk = ctx->e2e_chunk;
-    const size_t nchunks = std::max<size_t>(1, (n + chunk - 1) / chunk);
+    // chunk schedule: the downloads cannot start before the first chunk is up and indexed, so the pipeline ramps
+    // up (chunk/8, chunk/4, chunk/2, then full chunks) instead of paying a full chunk of upload time as fill latency
+    // (measured: 27.16 vs 27.28 ms per GiB of cfg2 -- the step is bound by the D2H volume, the fill is ~1 ms of it)
+    std::vector<size_t> chunk_off;
+    {
+        const size_t full = ctx->e2e_chunk;
+        size_t off = 0, len = ctx->e2e_ramp ? std::max<size_t>(full / 8, 1u << 20) : full;
+        len = (len + 127) & ~size_t(127);   // chunk boundaries stay 128-byte aligned (TMA rows)
+        while (off < n) {
+            chunk_off.push_back(off);
+            off += std::min(len, n - off);
+            len = std::min(full, len * 2);
+        }
+        if (chunk_off.empty()) chunk_off.push_back(0);   // an empty shard still runs one empty launch
+        chunk_off.push_back(n);
+    }
+    const size_t nchunks = chunk_off.size() - 1;
     if (nchunks + 1 >= kRingCells) return fail(ctx, CSVB200_ERR_INVALID_ARG, "input too large for the chunk pipeline");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s_up = ctx->stream, s_down = ctx->copy_stream;
@@ -562,7 +578,7 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
     };
     // ---- enqueue every upload + launch; nothing here waits on the host ----
     for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
-        const size_t off = c * chunk, len = std::min(chunk, n - off);
+        const size_t off = chunk_off[c], len = chunk_off[c + 1] - off;
         if (!o.d_bytes_in) rc = upload(ctx, d_bytes + off, host_bytes + off, len);
         if (rc) break;
         cudaError_t e = cudaSuccess;

@@ -51,6 +51,7 @@ struct csvb200_ctx {
     int kernel_override = 0;  // 0 = auto, 1 = simple, 2 = tma (CSVB200_KERNEL)
     uint32_t tune = 0;        // CSVB200_TUNE experiment knob
     bool host_result = true;  // kernels write {entries, end parity} straight into the pinned cell (CSVB200_HOST_RESULT=0: D2H copy node)
+    bool e2e_ramp = true;     // host -> host pipeline starts with small chunks (CSVB200_E2E_RAMP=0: uniform chunks)
     size_t e2e_chunk = csvb200::kE2eChunk;   // granularity of the host -> host pipeline (CSVB200_E2E_CHUNK_MB)
     std::string err;
 };
