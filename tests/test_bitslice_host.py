@@ -170,3 +170,74 @@ def test_utf8_slice_on_host():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "csv_simd_b200", "csrc"), src, "-o", exe])
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout[-2000:]
+
+
+UTF8_SO = r"""
+#include "utf8slice.cuh"
+#include <cstring>
+using namespace csvb200;
+// the kernel's decomposition on the host: 32-byte groups, utf8_check32 + halos, minimum of the starts (-1 = well-formed)
+extern "C" long sliced_valid_up_to(const uint8_t* s, long n)
+{
+    long best = -1;
+    for (long i0 = 0; i0 < n; i0 += 32) {
+        uint8_t g[32] = {0};
+        memcpy(g, s + i0, (size_t)((n - i0) < 32 ? (n - i0) : 32));
+        uint32_t w[8];
+        memcpy(w, g, 32);
+        const uint32_t b1 = i0 >= 1 ? s[i0 - 1] : 0, b2 = i0 >= 2 ? s[i0 - 2] : 0, b3 = i0 >= 3 ? s[i0 - 3] : 0;
+        const uint32_t n0 = i0 + 32 < n ? s[i0 + 32] : 0x100, n1 = i0 + 33 < n ? s[i0 + 33] : 0x100,
+                       n2 = i0 + 34 < n ? s[i0 + 34] : 0x100;
+        const uint32_t r = utf8_check32(w, utf8_owed(b1, b2, b3), n0, n1, n2);
+        if (r != kUtf8None && (best < 0 || i0 + r < best)) best = i0 + r;
+    }
+    return best;
+}
+"""
+
+
+def test_utf8_slice_against_cpython_decoder():
+    """The same rule engine, directly against CPython's strict UTF-8 decoder (= core::str::from_utf8's table and
+    error position) on random and crafted inputs -- pins K7's logic on the CPU, no GPU involved."""
+    import ctypes as C
+    import random
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "u.cpp")
+        open(src, "w").write(UTF8_SO)
+        so = os.path.join(d, "libu.so")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "csv_simd_b200", "csrc"),
+                               src, "-o", so])
+        L = C.CDLL(so)
+        L.sliced_valid_up_to.argtypes = [C.c_char_p, C.c_long]
+        L.sliced_valid_up_to.restype = C.c_long
+
+        def want(b):
+            try:
+                b.decode("utf-8")
+                return -1
+            except UnicodeDecodeError as e:
+                return e.start
+
+        rnd = random.Random(3)
+        tricky = [0x41, 0x80, 0x8F, 0x90, 0x9F, 0xA0, 0xBF, 0xC0, 0xC1, 0xC2, 0xDF, 0xE0, 0xE1, 0xED, 0xEE, 0xEF, 0xF0, 0xF1,
+                  0xF4, 0xF5, 0xFF]
+        texts = ["naïve café", "日本語のテキスト", "🙂🙃 emoji", "αβγ,δεζ\n", "퟿\U0010ffff\U00010000ࠀ߿"]
+        n_bad = 0
+        for it in range(20000):
+            mode = it % 4
+            if mode == 0:
+                b = bytes(rnd.choice(tricky) if rnd.random() < 0.3 else 0x61 for _ in range(rnd.randrange(1, 120)))
+            elif mode == 1:
+                b = bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 80)))
+            elif mode == 2:       # valid text with one byte damaged
+                t = bytearray(("x" * rnd.randrange(0, 40) + rnd.choice(texts) * rnd.randrange(1, 4)).encode())
+                t[rnd.randrange(len(t))] = rnd.choice(tricky)
+                b = bytes(t)
+            else:                 # valid text, possibly truncated mid-sequence
+                t = ("y" * rnd.randrange(0, 40) + rnd.choice(texts) * rnd.randrange(1, 4)).encode()
+                b = t[:rnd.randrange(1, len(t) + 1)]
+            got = L.sliced_valid_up_to(b, len(b))
+            if got != want(b):
+                n_bad += 1
+                assert n_bad < 3, (b, got, want(b))
+        assert n_bad == 0
