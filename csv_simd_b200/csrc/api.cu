@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libcsvb200 (see include/csvb200.h): context, streams, pinned
 // staging, index objects, Tape metadata and lookup entry points.  Host orchestration only;
-// all compute is in index_build.cu / lookup.cu.  There is deliberately no CPU fallback:
+// all compute is in the kernels (index_build_tma.cu, index_build.cu, lookup.cu, tape.cu, materialize.cu,
+// validate.cu); stream.cu holds the streaming-ingest half of the ABI.  There is deliberately no CPU fallback:
 // every compute entry point returns CSVB200_ERR_CUDA when the device path is unavailable.
 #include <cuda_runtime.h>
 

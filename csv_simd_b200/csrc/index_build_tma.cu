@@ -18,6 +18,9 @@
 //     look-back latency is covered by useful work instead of a barrier stall;
 //   * every descriptor sits in its own 128-byte line (internal.h kDescStride): hundreds of CTAs poll
 //     the same few hundred descriptors and packed descriptors serialise on a handful of L2 slices;
+//   * the thread that resolves tile 0 writes the sentinel index[0] = 0 (src/reader.rs:216) and the one that resolves
+//     the last tile writes {entries, end parity} both to the device cell and to its pinned host mirror, so a build is
+//     ONE launch with no memset / copy nodes around it except the zeroing of the look-back scratch;
 //   * the input is a 2-D tensor map [rows = n/128][128 B]; rows past the end are zero-filled by the
 //     TMA unit, which reproduces the reference's zero padding of the last block
 //     (src/avx/stage1.rs:54-88) for free; the sub-row tail (< 128 B) is patched in by one thread.
