@@ -451,6 +451,19 @@ def test_speculative_shard_build(forced_ctxs):
         assert any(r[0] for r in redone) and not redone[0][0]
         assert [r[1] for r in redone] == [O.shard_summary(raw2[:k])[0] for k in cuts2[:-1]]
         assert [f[0] + (k == 0) for k, f in enumerate(fin)] == lens
+        # SURVEY 8d forced boundaries: inside a quoted field, between the two quotes of "", between CR and LF
+        body = b'id,"text, with ""escapes"" and\r\nnewlines",tail\r\n' * 4000
+        raw4 = b"h1,h2,h3\r\n" + body
+        want4 = O.closed_form_numpy(raw4)
+        inside = raw4.index(b"text")
+        esc = raw4.index(b'""') + 1
+        crlf = raw4.index(b"\r\n", 50) + 1
+        for cut in (inside, esc, crlf, inside + 48 * 1000, esc + 48 * 2001, crlf + 48 * 3999):
+            got, redone, fin, lens = _speculative_chain(c, raw4, [0, cut, len(raw4)], dev)
+            assert got.shape == want4.shape and (got == want4).all(), cut
+            assert redone[1][1] == O.shard_summary(raw4[:cut])[0]
+        got, redone, fin, lens = _speculative_chain(c, raw4, [0, inside, esc, crlf, len(raw4) // 2 + 5, len(raw4)], dev)
+        assert (got == want4).all()
         # no quote at all inside the window / empty shard / tiny shards
         raw3 = b"1,2,3\n" * 30000
         got, redone, fin, lens = _speculative_chain(c, raw3, [0, 7, 7, 100, 100000, len(raw3)], dev, window=4096)
