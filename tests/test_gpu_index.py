@@ -898,3 +898,41 @@ def test_index_wrap_device(ctx):
         w2.tape_validate(8, True)
     w2.free()
     built.free()
+
+
+def test_more_than_2_pow_32_entries(ctx):
+    """Maximum-size edge (SURVEY 8c quirk ii): the reference's `array_idx: u32` wraps once the index holds 2^32
+    entries; here the count travels as 61 bits through the look-back chain.  4.3 G separators in one launch: the
+    entry count and sampled entries on both sides of slot 2^32 are checked on the device (index = 34 GB)."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    free, _ = torch.cuda.mem_get_info(dev)
+    n = (1 << 32) + (3 << 20) + 77
+    if free < 9 * n + (8 << 30):
+        pytest.skip("needs ~45 GB of free device memory")
+    d = torch.full((n + 64,), 0x2C, dtype=torch.uint8, device=dev)
+    d[n - 1] = 0x0A
+    ctx.set_reserve(1, 1)                      # one entry per byte is the worst case: no overflow rebuild
+    try:
+        idx = ctx.index_build_device(d.data_ptr(), n)
+        E = len(idx)
+        assert E == n + 1 and E > (1 << 32)
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (E,), "typestr": "<i8", "data": (idx.device_ptr, False), "version": 2}
+        entries = torch.as_tensor(_Raw(), device=dev)
+        probe = torch.cat([torch.arange(0, 4096, device=dev), torch.arange((1 << 32) - 4096, (1 << 32) + 4096, device=dev),
+                           torch.arange(E - 4096, E, device=dev),
+                           torch.randint(1, E, (1 << 20,), device=dev, generator=torch.Generator(device=dev).manual_seed(1))])
+        got = entries[probe]
+        want = torch.clamp(probe - 1, min=0)     # entry k (k >= 1) is byte k - 1; the sentinel is 0
+        assert bool((got == want).all())
+        # sortedness of the whole index without bringing it to the host: every difference is exactly 1 after the sentinel
+        step = 1 << 28
+        for lo in range(1, E - 1, step):
+            hi = min(lo + step, E - 1)
+            assert bool((entries[lo + 1:hi + 1] - entries[lo:hi] == 1).all())
+        idx.free()
+    finally:
+        ctx.set_reserve(1, 3)
+        del d
+        torch.cuda.empty_cache()
