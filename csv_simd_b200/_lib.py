@@ -38,6 +38,16 @@ class TapeReport(C.Structure):
                 ("record_cnt", C.c_uint32), ("ok", C.c_uint32)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("base", C.c_uint64), ("entries", C.c_uint64), ("epoch", C.c_uint64), ("carry_in", C.c_uint32),
+                ("redone", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32)]
+
+
+class MultiStats(C.Structure):
+    _fields_ = [("seconds", C.c_double), ("upload_seconds", C.c_double), ("download_seconds", C.c_double),
+                ("entries", C.c_uint64), ("redone_mask", C.c_uint32), ("carry_mask", C.c_uint32)]
+
+
 class Chunk(C.Structure):
     _fields_ = [("start", C.c_uint64), ("end", C.c_uint64), ("byte_start", C.c_uint64), ("byte_end", C.c_uint64),
                 ("record_cnt", C.c_uint32), ("id", C.c_uint8)]
@@ -77,6 +87,24 @@ SIGNATURES = {
                                               C.c_void_p, C.c_size_t, szp, C.c_void_p, vpp]),
     "csvb200_shard_job_verify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, szp, C.POINTER(C.c_int)]),
     "csvb200_shard_job_free": (None, [C.c_void_p]),
+    "csvb200_exchange_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, vpp]),
+    "csvb200_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "csvb200_exchange_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "csvb200_exchange_connect_local": (C.c_int, [vpp, C.c_uint32]),
+    "csvb200_exchange_destroy": (None, [C.c_void_p]),
+    "csvb200_index_build_shard_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64,
+                                                     C.c_uint64, vpp]),
+    "csvb200_index_shard_info": (C.c_int, [C.c_void_p, C.POINTER(ShardInfo)]),
+    "csvb200_exchange_counts": (C.c_int, [C.c_void_p, C.c_void_p, u64p, u32p]),
+    "csvb200_shard_build_to_host_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64,
+                                                       C.c_void_p, C.c_size_t, szp, C.POINTER(ShardInfo), u64p, u32p]),
+    "csvb200_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, vpp]),
+    "csvb200_multi_destroy": (None, [C.c_void_p]),
+    "csvb200_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "csvb200_multi_device_count": (C.c_int, [C.c_void_p]),
+    "csvb200_multi_index_build_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, szp, C.c_void_p, C.c_size_t,
+                                                    szp]),
+    "csvb200_multi_last_stats": (C.c_int, [C.c_void_p, C.POINTER(MultiStats)]),
     "csvb200_index_wrap_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, vpp]),
     "csvb200_index_sync": (C.c_int, [C.c_void_p]),
     "csvb200_index_len": (C.c_size_t, [C.c_void_p]),

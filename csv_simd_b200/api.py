@@ -118,6 +118,8 @@ class Context:
             try:
                 b = read(cap)
                 k = len(b)
+                if k > cap:   # checked BEFORE the copy: dst is a pinned ring slot of exactly `cap` bytes
+                    raise ValueError(f"read({cap}) returned {k} bytes")
                 if k:
                     C.memmove(dst, bytes(b) if not isinstance(b, (bytes, bytearray)) else b, k)
                 return k
@@ -218,6 +220,32 @@ class Context:
         self._check(rc)
         return ln.value, bool(redone.value)
 
+    # -- the exchange: peer-mapped mailboxes instead of a collective (include/csvb200.h) ---------------------
+    def exchange(self, rank: int, world: int) -> "Exchange":
+        return Exchange(self, rank, world)
+
+    def index_build_shard_exchange(self, ex: "Exchange", dev_ptr: int, n: int, global_offset: int,
+                                   predict_window: int = 0) -> "StructureIndex":
+        """Prediction, build, in-kernel exchange and conditional re-index of this rank's shard: one call, nothing
+        waits on the host.  COLLECTIVE: every rank calls it in the same order."""
+        h = C.c_void_p()
+        self._check(self._lib.csvb200_index_build_shard_exchange(self._h, ex._h, C.c_void_p(dev_ptr), n, global_offset,
+                                                                 predict_window, C.byref(h)))
+        idx = StructureIndex(self, h)
+        idx._exchange = ex
+        return idx
+
+    def shard_build_to_host_exchange(self, ex: "Exchange", host_ptr: int, n: int, global_offset: int, dst_ptr: int,
+                                     dst_cap: int, want_counts: bool = False):
+        """End-to-end form -> (entries in dst, info dict, counts per rank or None)."""
+        ln = C.c_size_t()
+        info = _lib.ShardInfo()
+        counts = (C.c_uint64 * ex.world)() if want_counts else None
+        self._check(self._lib.csvb200_shard_build_to_host_exchange(self._h, ex._h, C.c_void_p(host_ptr), n, global_offset,
+                                                                   C.c_void_p(dst_ptr), dst_cap, C.byref(ln), C.byref(info),
+                                                                   counts, None))
+        return ln.value, {k: int(getattr(info, k)) for k, _ in _lib.ShardInfo._fields_}, (list(counts) if counts else None)
+
     def index_wrap_device(self, d_entries: int, length: int, input_bytes: int, d_bytes: int = 0) -> "StructureIndex":
         """csvb200_index_wrap_device: an index object over caller-owned device entries (not freed with it)."""
         h = C.c_void_p()
@@ -258,6 +286,103 @@ class Context:
         out = np.zeros(a.size, dtype=np.uint8)
         self._check(self._lib.csvb200_class_bytes(self._h, a.ctypes.data, a.size, out.ctypes.data))
         return out
+
+
+class Exchange:
+    """csvb200_exchange: this rank's endpoint of the mailbox exchange.  handle() -> 64 bytes to give to every peer;
+    connect(handles) maps the peers' mailboxes (CUDA IPC between processes of one node)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        ctx._check(self._lib.csvb200_exchange_create(ctx._h, self.rank, self.world, C.byref(h)))
+        self._h = h
+
+    def handle(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self.ctx._check(self._lib.csvb200_exchange_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles):
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * self.world
+        self.ctx._check(self._lib.csvb200_exchange_connect(self._h, blob))
+
+    @staticmethod
+    def connect_local(exchanges):
+        arr = (C.c_void_p * len(exchanges))(*[e._h for e in exchanges])
+        rc = exchanges[0]._lib.csvb200_exchange_connect_local(arr, len(exchanges))
+        for e in exchanges:
+            if rc:
+                e.ctx._check(rc)
+
+    def counts(self, idx: "StructureIndex"):
+        """Host-side wait for every rank's row of that build -> (entries per rank, carry-in per rank)."""
+        counts = (C.c_uint64 * self.world)()
+        carries = (C.c_uint32 * self.world)()
+        self.ctx._check(self._lib.csvb200_exchange_counts(self._h, idx._h, counts, carries))
+        return list(counts), list(carries)
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self._lib.csvb200_exchange_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Multi:
+    """csvb200_multi: every listed GPU of THIS process behind one call (one host thread per device inside the
+    library): host bytes in, ONE contiguous host index out -- reader::read (src/reader.rs:150) at N GPUs."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self._lib.csvb200_multi_create(devs, len(devices), C.byref(h))
+        raise_for(rc, f"csvb200_multi_create({list(devices)}) failed")
+        self._h = h
+        self.devices = list(devices)
+
+    def index_build_to_host(self, host_ptr: int, n: int, dst_ptr: int, dst_cap: int, cuts=None) -> int:
+        ln = C.c_size_t()
+        c = (C.c_size_t * len(cuts))(*cuts) if cuts is not None else None
+        rc = self._lib.csvb200_multi_index_build_to_host(self._h, C.c_void_p(host_ptr), n, c, C.c_void_p(dst_ptr),
+                                                         dst_cap, C.byref(ln))
+        if rc:
+            raise_for(rc, self._lib.csvb200_multi_last_error(self._h).decode("utf-8", "replace"))
+        return ln.value
+
+    def index_build(self, data, cuts=None) -> np.ndarray:
+        a = _as_u8(data)
+        out = np.empty(a.size // 2 + 4096, dtype=np.uint64)
+        try:
+            ln = self.index_build_to_host(a.ctypes.data, a.size, out.ctypes.data, out.size, cuts)
+        except BufferError:
+            out = np.empty(a.size + 2, dtype=np.uint64)
+            ln = self.index_build_to_host(a.ctypes.data, a.size, out.ctypes.data, out.size, cuts)
+        return out[:ln]
+
+    def stats(self) -> dict:
+        st = _lib.MultiStats()
+        self._lib.csvb200_multi_last_stats(self._h, C.byref(st))
+        return {k: getattr(st, k) for k, _ in _lib.MultiStats._fields_}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.csvb200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class StructureIndex:
@@ -313,6 +438,12 @@ class StructureIndex:
     def shard_verify(self, d_gathered: int, world: int, d_final_out: int = 0):
         self.ctx._check(self._lib.csvb200_index_shard_verify(self._h, C.c_void_p(d_gathered), world,
                                                              C.c_void_p(d_final_out or 0)))
+
+    def shard_info(self) -> dict:
+        """csvb200_index_shard_info (exchange builds): base slot, entries, true carry-in, whether it was re-indexed."""
+        info = _lib.ShardInfo()
+        self.ctx._check(self._lib.csvb200_index_shard_info(self._h, C.byref(info)))
+        return {k: int(getattr(info, k)) for k, _ in _lib.ShardInfo._fields_}
 
     def shard_redone(self):
         """(misprediction rebuild ran?, true carry-in parity) of a speculative shard build."""

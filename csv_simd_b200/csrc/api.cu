@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <string>
 #include <vector>
@@ -38,6 +39,34 @@ bool is_pinned(const void* p)
     const bool ok = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     return ok;
+}
+
+size_t cell_alloc(csvb200_ctx* ctx, size_t count)
+{
+    if (ctx->cell_busy.empty()) ctx->cell_busy.assign(kRingCells, 0);
+    if (count == 0 || count > kRingCells) return SIZE_MAX;
+    std::vector<uint8_t>& busy = ctx->cell_busy;
+    size_t start = ctx->cell_hint + count <= kRingCells ? ctx->cell_hint : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        size_t run = 0;
+        for (size_t i = start; i < kRingCells; ++i) {
+            run = busy[i] ? 0 : run + 1;
+            if (run == count) {
+                const size_t first = i + 1 - count;
+                std::fill(busy.begin() + first, busy.begin() + i + 1, (uint8_t)1);
+                ctx->cell_hint = i + 1 < kRingCells ? i + 1 : 0;
+                return first;
+            }
+        }
+        start = 0;
+    }
+    return SIZE_MAX;
+}
+
+void cell_release(csvb200_ctx* ctx, size_t first, size_t count)
+{
+    if (first == SIZE_MAX || first + count > ctx->cell_busy.size()) return;
+    std::fill(ctx->cell_busy.begin() + first, ctx->cell_busy.begin() + first + count, (uint8_t)0);
 }
 
 int ensure_scratch(csvb200_ctx* ctx, size_t bytes)
@@ -82,7 +111,12 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
         const size_t sbytes = 128 + num_tiles * kDescStride * sizeof(uint64_t);
         int rc = ensure_scratch(ctx, sbytes);
         if (rc) return rc;
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, ctx->stream));
+        // DEBUG (CSVB200_TUNE bit 0x400, timing experiments only): keep the descriptors of the previous build of the
+        // same bytes, so every look-back finds a published prefix on its first poll -- the kernel without its chain
+        const bool keep_desc = (ctx->tune & 0x400u) && ctx->dbg_desc_src == idx->src && ctx->dbg_desc_n == n;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, keep_desc ? 128 : sbytes, ctx->stream));
+        ctx->dbg_desc_src = idx->src;
+        ctx->dbg_desc_n = n;
         BuildParams p{};
         p.in = idx->src;
         p.n = n;
@@ -110,6 +144,18 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             p.result2_words = 4;
             if (redo) {
                 p.run_flag = reinterpret_cast<const uint32_t*>(d_carry + 3);
+            } else if (idx->ex) {
+                // exchange inside the launch: separator total and the "look-back role over" counter live in the
+                // zeroed head of the scratch; the last CTA posts the row and resolves the carry chain into d_carry
+                p.total_out = reinterpret_cast<unsigned long long*>(ctx->d_scratch + 8);
+                p.ex_done = reinterpret_cast<uint32_t*>(ctx->d_scratch + 4);
+                p.ex.peers = idx->ex->d_peers;
+                p.ex.rank = idx->ex->rank;
+                p.ex.world = idx->ex->world;
+                p.ex.epoch = idx->ex_epoch;
+                p.ex.timeout_ns = idx->ex->timeout_ns;
+                p.ex.out = d_carry;
+                p.ex.out_host = ctx->h_cells + idx->carry_cell * kCellWords;
             } else if (!idx->verified && idx->d_result2) {
                 // first (speculative) launch: also accumulate the shard's separator total
                 CU_TRY(ctx, cudaMemsetAsync(idx->d_result2, 0, 4 * sizeof(uint64_t), ctx->stream));
@@ -144,10 +190,14 @@ int new_index(csvb200_ctx* ctx, csvb200_index** out)
     csvb200_index* idx = new (std::nothrow) csvb200_index();
     if (!idx) return fail(ctx, CSVB200_ERR_OOM, "host allocation failed");
     idx->ctx = ctx;
-    idx->cell = ctx->next_cell;
-    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+    idx->cell = cell_alloc(ctx, 1);
+    if (idx->cell == SIZE_MAX) {
+        delete idx;
+        return fail(ctx, CSVB200_ERR_OOM, "too many live index objects in this context (4095 result cells)");
+    }
     cudaError_t e = cudaEventCreateWithFlags(&idx->done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
+        cell_release(ctx, idx->cell, 1);
         delete idx;
         return fail(ctx, CSVB200_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
     }
@@ -158,7 +208,7 @@ int new_index(csvb200_ctx* ctx, csvb200_index** out)
 int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity, uint64_t pos_bias,
                         int emit_sentinel, csvb200_index** out, const uint32_t* d_shard_par = nullptr,
                         uint32_t shard_rank = 0, uint64_t* d_result2 = nullptr, bool speculative = false,
-                        uint64_t predict_window = 0)
+                        uint64_t predict_window = 0, csvb200_exchange* ex = nullptr)
 {
     if (!ctx || !out || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     if ((reinterpret_cast<uintptr_t>(dev_bytes) & 15u) != 0)
@@ -175,11 +225,18 @@ int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint3
     idx->d_shard_par = d_shard_par;
     idx->shard_rank = shard_rank;
     idx->d_result2 = d_result2;
+    if (ex) {
+        idx->ex = ex;
+        idx->ex_epoch = ++ex->epoch;
+    }
     if (speculative) {
         // predicted carry-in parity (rank 0: known to be 0) in a device cell the build launch reads
+        idx->carry_cell = cell_alloc(ctx, 1);
+        if (idx->carry_cell == SIZE_MAX) {
+            csvb200_index_free(idx);
+            return fail(ctx, CSVB200_ERR_OOM, "too many live index objects in this context (4095 result cells)");
+        }
         idx->speculative = true;
-        idx->carry_cell = ctx->next_cell;
-        ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
         uint64_t* d_carry = ctx->d_cells + idx->carry_cell * kCellWords;
         cudaError_t e = cudaSuccess;
         if (shard_rank == 0 || n == 0) {
@@ -202,6 +259,11 @@ int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint3
         return fail(ctx, CSVB200_ERR_OOM, std::string("index allocation: ") + cudaGetErrorString(e));
     }
     rc = enqueue_build(idx, true);
+    if (!rc && ex) {
+        // the rebuild with the true carry is enqueued unconditionally and exits at once when the flag is 0
+        idx->verified = true;
+        rc = enqueue_build(idx, false, true);
+    }
     if (rc) {
         csvb200_index_free(idx);
         return rc;
@@ -243,6 +305,52 @@ int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n)
     return CSVB200_OK;
 }
 
+int ensure_bounce(csvb200_ctx* ctx)
+{
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaSuccess;
+        if (!ctx->h_bounce[i]) e = cudaHostAlloc((void**)&ctx->h_bounce[i], kBounceEntries * sizeof(uint64_t), cudaHostAllocDefault);
+        if (e == cudaSuccess && !ctx->bounce_done[i]) e = cudaEventCreateWithFlags(&ctx->bounce_done[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, CSVB200_ERR_OOM, std::string("bounce buffers: ") + cudaGetErrorString(e));
+        }
+    }
+    return CSVB200_OK;
+}
+
+int download(csvb200_ctx* ctx, uint64_t* dst, const uint64_t* d_src, size_t count)
+{
+    if (count == 0) return CSVB200_OK;
+    if (!dst || !d_src) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (is_pinned(dst)) {
+        CU_TRY(ctx, cudaMemcpyAsync(dst, d_src, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return CSVB200_OK;
+    }
+    int rc = ensure_bounce(ctx);
+    if (rc) return rc;
+    size_t pos[2] = {0, 0}, len[2] = {0, 0}, issued = 0, flushed = 0;
+    auto flush = [&](size_t k) -> cudaError_t {
+        const int b = (int)(k & 1);
+        cudaError_t e = cudaEventSynchronize(ctx->bounce_done[b]);
+        if (e == cudaSuccess) parallel_memcpy(io_pool(ctx), dst + pos[b], ctx->h_bounce[b], len[b] * sizeof(uint64_t));
+        return e;
+    };
+    for (size_t off = 0; off < count; off += kBounceEntries) {
+        const int b = (int)(issued & 1);
+        if (issued >= 2) CU_TRY(ctx, flush(flushed++));
+        pos[b] = off;
+        len[b] = std::min(kBounceEntries, count - off);
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_bounce[b], d_src + off, len[b] * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaEventRecord(ctx->bounce_done[b], ctx->stream));
+        ++issued;
+    }
+    while (flushed < issued) CU_TRY(ctx, flush(flushed++));
+    return CSVB200_OK;
+}
+
 }  // namespace csvb200
 
 extern "C" {
@@ -263,6 +371,7 @@ const char* csvb200_status_string(int s)
     case CSVB200_ERR_INPUT_TOO_SMALL: return "input shorter than 64 bytes";
     case CSVB200_ERR_CAPACITY: return "destination capacity too small";
     case CSVB200_ERR_OUT_OF_BOUNDS: return "index slot out of bounds";
+    case CSVB200_ERR_EXCHANGE: return "cross-GPU exchange failed";
     default: return "unknown status";
     }
 }
@@ -425,6 +534,33 @@ int csvb200_index_build_shard_speculative(csvb200_ctx* ctx, const void* dev_byte
                                true, predict_window);
 }
 
+int csvb200_index_build_shard_exchange(csvb200_ctx* ctx, csvb200_exchange* ex, const void* dev_bytes, size_t n,
+                                       uint64_t global_offset, uint64_t predict_window, csvb200_index** out)
+{
+    if (!ctx || !ex || ex->ctx != ctx) return fail(ctx, CSVB200_ERR_INVALID_ARG, "exchange does not belong to this context");
+    if (!ex->connected) return fail(ctx, CSVB200_ERR_INVALID_STATE, "exchange is not connected");
+    return build_device_common(ctx, dev_bytes, n, 0u, global_offset, ex->rank == 0 ? 1 : 0, out, nullptr, ex->rank, nullptr,
+                               true, predict_window, ex);
+}
+
+int csvb200_index_shard_info(csvb200_index* idx, csvb200_shard_info* out)
+{
+    if (!idx || !out) return CSVB200_ERR_INVALID_ARG;
+    if (!idx->ex) return fail(idx->ctx, CSVB200_ERR_INVALID_STATE, "index was not built through an exchange");
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    const uint64_t* h_carry = idx->ctx->h_cells + idx->carry_cell * kCellWords;
+    const uint64_t below = h_carry[2] & ~(1ull << 63);
+    out->entries = idx->len;
+    out->base = idx->ex->rank == 0 ? 0 : 1 + below;
+    out->carry_in = (uint32_t)(h_carry[1] & 1u);
+    out->redone = (uint32_t)(h_carry[3] & 1u);
+    out->rank = idx->ex->rank;
+    out->world = idx->ex->world;
+    out->epoch = idx->ex_epoch;
+    return CSVB200_OK;
+}
+
 int csvb200_index_shard_verify(csvb200_index* idx, const uint64_t* d_gathered, uint32_t world, uint64_t* d_final_out)
 {
     if (!idx) return CSVB200_ERR_INVALID_ARG;
@@ -473,23 +609,20 @@ int csvb200_index_build(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, u
     if ((flags & CSVB200_BUILD_STRICT_MIN64) && n < 64)
         return fail(ctx, CSVB200_ERR_INPUT_TOO_SMALL, "n < 64: the reference panics on this input");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    uint8_t* d_bytes = nullptr;
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, ctx->stream));
-    int rc = upload(ctx, d_bytes, host_bytes, n);
+    DevBuf d_bytes;
+    CU_TRY(ctx, d_bytes.alloc(((n + 15) & ~size_t(15)) + 16, ctx->stream));
+    int rc = upload(ctx, d_bytes.as<uint8_t>(), host_bytes, n);
     csvb200_index* idx = nullptr;
-    if (!rc) rc = build_device_common(ctx, d_bytes, n, 0u, 0ull, 1, &idx);
+    if (!rc) rc = build_device_common(ctx, d_bytes.p, n, 0u, 0ull, 1, &idx);
     if (!rc) rc = csvb200_index_sync(idx);  // resolves a capacity overflow while the bytes are still here
     if (rc) {
         if (idx) csvb200_index_free(idx);
-        cudaFreeAsync(d_bytes, ctx->stream);
         return rc;
     }
-    if (flags & CSVB200_BUILD_KEEP_BYTES) {
-        idx->d_bytes_owned = d_bytes;
-    } else {
-        CU_TRY(ctx, cudaFreeAsync(d_bytes, ctx->stream));
-        idx->src = nullptr;
-    }
+    if (flags & CSVB200_BUILD_KEEP_BYTES)
+        idx->d_bytes_owned = static_cast<uint8_t*>(d_bytes.release());
+    else
+        idx->src = nullptr;   // d_bytes is released (stream-ordered) on return
     *out = idx;
     return CSVB200_OK;
 }
@@ -546,8 +679,11 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
         chunk_off.push_back(n);
     }
     const size_t nchunks = chunk_off.size() - 1;
-    if (nchunks + 1 >= kRingCells) return fail(ctx, CSVB200_ERR_INVALID_ARG, "input too large for the chunk pipeline");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    // cells: cell0 = carry into chunk 0; cell[c+1] = result of chunk c (held until this call returns)
+    CellLease lease(ctx, nchunks + 1);
+    if (!lease.ok()) return fail(ctx, CSVB200_ERR_OOM, "not enough free result cells for the chunk pipeline");
+    const size_t cell0 = lease.first;
     cudaStream_t s_up = ctx->stream, s_down = ctx->copy_stream;
     uint8_t* d_bytes = const_cast<uint8_t*>(o.d_bytes_in);
     uint64_t* d_index = nullptr;
@@ -555,9 +691,6 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
     const uint64_t out_base = o.emit_sentinel ? 1 : 0;
     if (!d_bytes) CU_TRY(ctx, cudaMallocAsync((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, s_up));
     CU_TRY(ctx, cudaMallocAsync((void**)&d_index, cap * sizeof(uint64_t), s_up));
-    // cells: cell0 = carry into chunk 0; cell[c+1] = result of chunk c
-    const size_t cell0 = ctx->next_cell + nchunks + 1 <= kRingCells ? ctx->next_cell : 0;
-    ctx->next_cell = (cell0 + nchunks + 1) % kRingCells;
     uint64_t* d_cells = ctx->d_cells + cell0 * kCellWords;
     uint64_t* h_cells = ctx->h_cells + cell0 * kCellWords;
     if (o.d_carry0)
@@ -638,17 +771,7 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
     // synchronous driver-staged transfer, so its segments come down into two pinned bounce buffers and the
     // context's host threads move them on while the next piece is in flight.
     const bool bounce = dst != nullptr && !is_pinned(dst);
-    if (bounce) {
-        for (int i = 0; i < 2 && rc == CSVB200_OK; ++i) {
-            cudaError_t e = cudaSuccess;
-            if (!ctx->h_bounce[i]) e = cudaHostAlloc((void**)&ctx->h_bounce[i], kBounceEntries * sizeof(uint64_t), cudaHostAllocDefault);
-            if (e == cudaSuccess && !ctx->bounce_done[i]) e = cudaEventCreateWithFlags(&ctx->bounce_done[i], cudaEventDisableTiming);
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                rc = fail(ctx, CSVB200_ERR_OOM, std::string("bounce buffers: ") + cudaGetErrorString(e));
-            }
-        }
-    }
+    if (bounce && rc == CSVB200_OK) rc = ensure_bounce(ctx);
     size_t piece_pos[2] = {0, 0}, piece_len[2] = {0, 0}, pieces = 0, flushed = 0;
     auto flush_piece = [&](size_t k) -> cudaError_t {   // piece k (in order): wait for its D2H, copy it to dst
         const int b = (int)(k & 1);
@@ -761,8 +884,11 @@ int csvb200_shard_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
     job->dst = dst;
     job->dst_cap = dst_cap;
     job->d_result4 = d_result_out;
-    job->carry_cell = ctx->next_cell;
-    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+    job->carry_cell = cell_alloc(ctx, 1);
+    if (job->carry_cell == SIZE_MAX) {
+        delete job;
+        return fail(ctx, CSVB200_ERR_OOM, "too many live objects in this context (4095 result cells)");
+    }
     PipeOpts o;
     o.pos_bias = global_offset;
     o.emit_sentinel = emit_sentinel;
@@ -784,6 +910,7 @@ int csvb200_shard_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
     }
     if (rc) {
         if (job->d_bytes) cudaFreeAsync(job->d_bytes, ctx->stream);
+        cell_release(ctx, job->carry_cell, 1);
         delete job;
         return rc;
     }
@@ -833,7 +960,75 @@ void csvb200_shard_job_free(csvb200_shard_job* job)
     cudaSetDevice(job->ctx->device);
     if (job->d_bytes) cudaFreeAsync(job->d_bytes, job->ctx->stream);
     cudaGetLastError();
+    cell_release(job->ctx, job->carry_cell, 1);
     delete job;
+}
+
+int csvb200_shard_build_to_host_exchange(csvb200_ctx* ctx, csvb200_exchange* ex, const uint8_t* host_bytes, size_t n,
+                                         uint64_t global_offset, uint64_t* dst, size_t dst_cap, size_t* len_out,
+                                         csvb200_shard_info* info, uint64_t* counts, uint32_t* carries)
+{
+    if (!ctx || !ex || ex->ctx != ctx || !len_out) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument / foreign exchange");
+    if (!ex->connected) return fail(ctx, CSVB200_ERR_INVALID_STATE, "exchange is not connected");
+    // 1. the shard goes up, is indexed and comes down chunk by chunk under the predicted carry
+    csvb200_shard_job* job = nullptr;
+    int rc = csvb200_shard_build_to_host(ctx, host_bytes, n, ex->rank, global_offset, ex->rank == 0 ? 1 : 0, dst, dst_cap, len_out,
+                                         ex->d_row4, &job);
+    if (rc) return rc;
+    // 2. post the row, resolve the lower ranks (one tiny launch; the pipeline's last chunk is not known in advance)
+    const uint64_t epoch = ++ex->epoch;
+    uint64_t* d_carry = ctx->d_cells + job->carry_cell * kCellWords;
+    uint64_t* h_carry = ctx->h_cells + job->carry_cell * kCellWords;
+    ExchangeArgs a{};
+    a.peers = ex->d_peers;
+    a.rank = ex->rank;
+    a.world = ex->world;
+    a.epoch = epoch;
+    a.timeout_ns = ex->timeout_ns;
+    a.out = d_carry;
+    a.out_host = h_carry;
+    cudaError_t e = launch_exchange(a, ex->d_row4, ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        csvb200_shard_job_free(job);
+        return fail(ctx, CSVB200_ERR_CUDA, std::string("exchange launch: ") + cudaGetErrorString(e));
+    }
+    if (h_carry[2] >> 63) {
+        csvb200_shard_job_free(job);
+        return fail(ctx, CSVB200_ERR_EXCHANGE, "exchange: a lower rank never posted its row for this build (timeout), or lapped the mailbox ring");
+    }
+    const bool redo = (h_carry[3] & 1u) != 0;
+    // 3. only a shard whose guess was wrong is indexed again, from the device copy the job kept
+    if (redo) {
+        PipeOpts o;
+        o.pos_bias = global_offset;
+        o.emit_sentinel = ex->rank == 0 ? 1 : 0;
+        o.d_carry0 = d_carry;
+        o.d_bytes_in = job->d_bytes;
+        bool overflow = false;
+        const uint32_t num = ctx->reserve_num, den = ctx->reserve_den;
+        ctx->reserve_num = 1;    // a flipped carry can turn every masked separator into an entry
+        ctx->reserve_den = 1;
+        rc = pipeline_to_host(ctx, host_bytes, n, dst, dst_cap, len_out, o, &overflow);
+        ctx->reserve_num = num;
+        ctx->reserve_den = den;
+    } else if (job->dst_small) {
+        rc = fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    }
+    if (info) {
+        info->entries = *len_out;
+        info->base = ex->rank == 0 ? 0 : 1 + (h_carry[2] & ~(1ull << 63));
+        info->carry_in = (uint32_t)(h_carry[1] & 1u);
+        info->redone = redo ? 1u : 0u;
+        info->rank = ex->rank;
+        info->world = ex->world;
+        info->epoch = epoch;
+    }
+    csvb200_shard_job_free(job);
+    if (!rc && (counts || carries)) rc = exchange_wait_all(ex, epoch, counts, carries);
+    return rc;
 }
 
 int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t* parity_out)
@@ -842,8 +1037,9 @@ int csvb200_shard_quote_parity(csvb200_ctx* ctx, const void* dev_bytes, size_t n
     if ((reinterpret_cast<uintptr_t>(dev_bytes) & 15u) != 0)
         return fail(ctx, CSVB200_ERR_INVALID_ARG, "device input must be 16-byte aligned");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t cell = ctx->next_cell;
-    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+    CellLease lease(ctx, 1);
+    if (!lease.ok()) return fail(ctx, CSVB200_ERR_OOM, "no free result cell (4095 live index objects)");
+    const size_t cell = lease.first;
     uint64_t* d_cell = ctx->d_cells + cell * kCellWords;
     uint64_t* h_cell = ctx->h_cells + cell * kCellWords;
     CU_TRY(ctx, cudaMemsetAsync(d_cell, 0, sizeof(uint64_t), ctx->stream));
@@ -887,6 +1083,8 @@ int csvb200_index_sync(csvb200_index* idx)
         const uint64_t* h_cell = ctx->h_cells + idx->cell * kCellWords;
         const size_t len = (size_t)(idx->out_base + h_cell[0]);
         idx->end_parity = (int)(h_cell[1] & 1u);
+        if (idx->ex && (ctx->h_cells[idx->carry_cell * kCellWords + 2] >> 63))
+            return fail(ctx, CSVB200_ERR_EXCHANGE, "exchange: a lower rank never posted its row for this build (timeout), or lapped the mailbox ring");
         if (len <= idx->cap) {
             idx->len = len;
             idx->synced = true;
@@ -943,6 +1141,9 @@ void csvb200_index_free(csvb200_index* idx)
     if (idx->d_bytes_owned) cudaFreeAsync(idx->d_bytes_owned, ctx->stream);
     if (idx->done) cudaEventDestroy(idx->done);
     cudaGetLastError();
+    // (a cell released while its launch is still in flight is safe: the next holder's launch follows it in stream order)
+    cell_release(ctx, idx->cell, 1);
+    if (idx->carry_cell != SIZE_MAX) cell_release(ctx, idx->carry_cell, 1);
     delete idx;
 }
 
@@ -977,8 +1178,9 @@ int csvb200_tape_validate(csvb200_index* idx, uint32_t field_cnt, int crlf, csvb
     const uint8_t* bytes = idx->d_bytes_owned ? idx->d_bytes_owned : idx->src;
     if (!bytes && idx->n) return fail(ctx, CSVB200_ERR_INVALID_STATE, "index was built without CSVB200_BUILD_KEEP_BYTES");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t cell = ctx->next_cell;
-    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+    CellLease lease(ctx, 1);
+    if (!lease.ok()) return fail(ctx, CSVB200_ERR_OOM, "no free result cell (4095 live index objects)");
+    const size_t cell = lease.first;
     uint64_t* d_cell = ctx->d_cells + cell * kCellWords;
     uint64_t* h_cell = ctx->h_cells + cell * kCellWords;
     CU_TRY(ctx, cudaMemsetAsync(d_cell, 0xff, sizeof(uint64_t), ctx->stream));
@@ -1047,16 +1249,14 @@ int csvb200_tape_chunks(csvb200_index* idx, uint8_t num, csvb200_chunk* out, siz
         slots[2 * i] = out[i].start;
         slots[2 * i + 1] = out[i].end;
     }
-    uint64_t *d_slots = nullptr, *d_vals = nullptr;
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_slots, slots.size() * 8, ctx->stream));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_vals, slots.size() * 8, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, launch_gather_slots(idx->d_index, idx->len, d_slots, slots.size(), d_vals, ctx->stream));
+    DevBuf d_slots, d_vals;
+    CU_TRY(ctx, d_slots.alloc(slots.size() * 8, ctx->stream));
+    CU_TRY(ctx, d_vals.alloc(slots.size() * 8, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_slots.p, slots.data(), slots.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, launch_gather_slots(idx->d_index, idx->len, d_slots.as<uint64_t>(), slots.size(), d_vals.as<uint64_t>(), ctx->stream));
     ctx->launches += 1;
-    CU_TRY(ctx, cudaMemcpyAsync(vals.data(), d_vals, slots.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(vals.data(), d_vals.p, slots.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(d_slots, ctx->stream);
-    cudaFreeAsync(d_vals, ctx->stream);
     for (size_t i = 0; i < nchunks; ++i) {
         out[i].byte_start = vals[2 * i] == UINT64_MAX ? UINT64_MAX : vals[2 * i] + 1;
         out[i].byte_end = vals[2 * i + 1] == UINT64_MAX ? UINT64_MAX : vals[2 * i + 1] + 1;
@@ -1277,30 +1477,31 @@ int csvb200_gather_fields(csvb200_index* idx, const uint32_t* rec, const uint32_
     std::vector<csvb200_range> ranges(nq);
     rc = seek_host(idx, rec, fld, nq, ranges.data());
     if (rc) return rc;
+    // positions are global; the bytes this index object holds are [pos_bias, pos_bias + n) (a shard of a sharded build)
+    const uint64_t lo = idx->pos_bias, hi = idx->pos_bias + idx->n;
     for (size_t i = 0; i < nq; ++i) {
         const csvb200_range& r = ranges[i];
         const uint64_t len = (r.start == UINT64_MAX || r.end < r.start) ? 0 : r.end - r.start;
+        if (len && (r.start < lo || r.end > hi))
+            return fail(ctx, CSVB200_ERR_OUT_OF_BOUNDS, "field lies outside the bytes this index object holds (another shard)");
         out_offsets[i + 1] = out_offsets[i] + len;
     }
     const uint64_t total = out_offsets[nq];
     if (total > out_cap) return fail(ctx, CSVB200_ERR_CAPACITY, "gather destination too small");
     if (total == 0) return CSVB200_OK;
     if (!out) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
-    uint64_t *d_ranges = nullptr, *d_off = nullptr;
-    uint8_t* d_out = nullptr;
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_ranges, nq * sizeof(csvb200_range), ctx->stream));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_off, (nq + 1) * sizeof(uint64_t), ctx->stream));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_out, total, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(d_ranges, ranges.data(), nq * sizeof(csvb200_range), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(d_off, out_offsets, (nq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf d_ranges, d_off, d_out;
+    CU_TRY(ctx, d_ranges.alloc(nq * sizeof(csvb200_range), ctx->stream));
+    CU_TRY(ctx, d_off.alloc((nq + 1) * sizeof(uint64_t), ctx->stream));
+    CU_TRY(ctx, d_out.alloc(total, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_ranges.p, ranges.data(), nq * sizeof(csvb200_range), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_off.p, out_offsets, (nq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     const uint8_t* bytes = idx->d_bytes_owned ? idx->d_bytes_owned : idx->src;
-    CU_TRY(ctx, launch_gather_bytes(bytes, d_ranges, d_off, nq, d_out, ctx->stream));
+    CU_TRY(ctx, launch_gather_bytes(bytes, idx->n, idx->pos_bias, d_ranges.as<uint64_t>(), d_off.as<uint64_t>(), nq,
+                                    d_out.as<uint8_t>(), ctx->stream));
     ctx->launches += 1;
-    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(d_ranges, ctx->stream);
-    cudaFreeAsync(d_off, ctx->stream);
-    cudaFreeAsync(d_out, ctx->stream);
     return CSVB200_OK;
 }
 
@@ -1369,33 +1570,23 @@ int csvb200_materialize_column(csvb200_index* idx, uint32_t field_idx, uint32_t 
     if (rc) return rc;
     csvb200_ctx* ctx = idx->ctx;
     if (!out_offsets || !out_len) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
-    uint64_t* d_off = nullptr;
-    uint8_t* d_out = nullptr;
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_off, ((size_t)nrec + 1) * sizeof(uint64_t), ctx->stream));
-    rc = materialize_enqueue(idx, field_idx, first_record, nrec, flags, d_off, nullptr, 0, true, false);
-    if (!rc) {
-        CU_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off, ((size_t)nrec + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        const uint64_t total = out_offsets[nrec];
-        *out_len = (size_t)total;
-        if (total > out_cap) {
-            rc = fail(ctx, CSVB200_ERR_CAPACITY, "materialize destination too small");
-        } else if (total > 0) {
-            if (!out) {
-                rc = fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
-            } else {
-                CU_TRY(ctx, cudaMallocAsync((void**)&d_out, total, ctx->stream));
-                rc = materialize_enqueue(idx, field_idx, first_record, nrec, flags, d_off, d_out, total, false, true);
-                if (!rc) {
-                    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
-                    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-                }
-            }
-        }
-    }
-    if (d_out) cudaFreeAsync(d_out, ctx->stream);
-    cudaFreeAsync(d_off, ctx->stream);
-    return rc;
+    DevBuf d_off, d_out;
+    CU_TRY(ctx, d_off.alloc(((size_t)nrec + 1) * sizeof(uint64_t), ctx->stream));
+    rc = materialize_enqueue(idx, field_idx, first_record, nrec, flags, d_off.as<uint64_t>(), nullptr, 0, true, false);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off.p, ((size_t)nrec + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t total = out_offsets[nrec];
+    *out_len = (size_t)total;
+    if (total > out_cap) return fail(ctx, CSVB200_ERR_CAPACITY, "materialize destination too small");
+    if (total == 0) return CSVB200_OK;
+    if (!out) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    CU_TRY(ctx, d_out.alloc(total, ctx->stream));
+    rc = materialize_enqueue(idx, field_idx, first_record, nrec, flags, d_off.as<uint64_t>(), d_out.as<uint8_t>(), total, false, true);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CSVB200_OK;
 }
 
 int csvb200_validate_utf8_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint64_t* d_result)
@@ -1413,11 +1604,13 @@ int csvb200_validate_utf8(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n,
 {
     if (!ctx || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    uint8_t* d_in = nullptr;
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_in, n + 16, ctx->stream));
+    DevBuf d_buf;
+    CU_TRY(ctx, d_buf.alloc(n + 16, ctx->stream));
+    uint8_t* d_in = d_buf.as<uint8_t>();
     int rc = upload(ctx, d_in, host_bytes, n);
-    const size_t cell = ctx->next_cell;
-    ctx->next_cell = (ctx->next_cell + 1) % kRingCells;
+    CellLease lease(ctx, 1);
+    if (!lease.ok()) return fail(ctx, CSVB200_ERR_OOM, "no free result cell (4095 live index objects)");
+    const size_t cell = lease.first;
     uint64_t* d_cell = ctx->d_cells + cell * kCellWords;
     uint64_t* h_cell = ctx->h_cells + cell * kCellWords;
     if (!rc) rc = csvb200_validate_utf8_device(ctx, d_in, n, d_cell);
@@ -1427,7 +1620,6 @@ int csvb200_validate_utf8(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n,
         if (valid_up_to) *valid_up_to = h_cell[0];
         if (is_ascii) *is_ascii = h_cell[1] ? 0 : 1;
     }
-    cudaFreeAsync(d_in, ctx->stream);
     return rc;
 }
 
@@ -1455,7 +1647,12 @@ int csvb200_index_save(csvb200_index* idx, const char* path)
     int rc = csvb200_index_sync(idx);
     if (rc) return rc;
     csvb200_ctx* ctx = idx->ctx;
-    std::vector<uint64_t> host(idx->len);
+    std::vector<uint64_t> host;
+    try {
+        host.resize(idx->len);
+    } catch (const std::exception&) {
+        return fail(ctx, CSVB200_ERR_OOM, "index does not fit in host memory");
+    }
     rc = csvb200_index_copy_out(idx, host.data(), host.size());
     if (rc) return rc;
     IndexFileHeader h{};
@@ -1489,17 +1686,25 @@ int csvb200_index_load(csvb200_ctx* ctx, const char* path, csvb200_index** out)
     if (ok) {
         std::fseek(f, 0, SEEK_END);
         const long long size = std::ftell(f);
-        ok = size >= 0 && (unsigned long long)size == sizeof(h) + h.entries * sizeof(uint64_t) && h.entries >= 1;
+        // entries is bounded by the file size BEFORE it is multiplied (a huge value must not wrap)
+        ok = size >= (long long)sizeof(h) && h.entries >= 1 &&
+             h.entries <= ((unsigned long long)size - sizeof(h)) / sizeof(uint64_t) &&
+             (unsigned long long)size == sizeof(h) + h.entries * sizeof(uint64_t);
         std::fseek(f, (long)sizeof(h), SEEK_SET);
     }
     if (ok) {
-        host.resize(h.entries);
+        try {
+            host.resize(h.entries);
+        } catch (const std::exception&) {   // nothing may unwind across the C ABI
+            std::fclose(f);
+            return fail(ctx, CSVB200_ERR_OOM, std::string(path) + ": index does not fit in host memory");
+        }
         ok = std::fread(host.data(), sizeof(uint64_t), host.size(), f) == host.size();
     }
     std::fclose(f);
     uint64_t sum = 0;
     for (uint64_t v : host) sum += v;
-    if (!ok || sum != h.checksum || host[0] != 0)
+    if (!ok || host.empty() || sum != h.checksum || host[0] != 0)
         return fail(ctx, CSVB200_ERR_INVALID_CSV_FORMAT, std::string(path) + ": not a csvb200 index file (bad magic, size or checksum)");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     csvb200_index* idx = nullptr;
@@ -1536,21 +1741,17 @@ int csvb200_block_masks(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, u
     if (n == 0) return CSVB200_OK;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t nb = (n + 63) / 64;
-    uint8_t* d_in = nullptr;
-    uint64_t *d_q = nullptr, *d_s = nullptr;
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_in, n, ctx->stream));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_q, nb * 8, ctx->stream));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_s, nb * 8, ctx->stream));
-    int rc = upload(ctx, d_in, host_bytes, n);
+    DevBuf d_in, d_q, d_s;
+    CU_TRY(ctx, d_in.alloc(n, ctx->stream));
+    CU_TRY(ctx, d_q.alloc(nb * 8, ctx->stream));
+    CU_TRY(ctx, d_s.alloc(nb * 8, ctx->stream));
+    int rc = upload(ctx, d_in.as<uint8_t>(), host_bytes, n);
     if (rc) return rc;
-    CU_TRY(ctx, launch_block_masks(d_in, n, d_q, d_s, ctx->stream));
+    CU_TRY(ctx, launch_block_masks(d_in.as<uint8_t>(), n, d_q.as<uint64_t>(), d_s.as<uint64_t>(), ctx->stream));
     ctx->launches += 1;
-    CU_TRY(ctx, cudaMemcpyAsync(quote_words, d_q, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(sep_words, d_s, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(quote_words, d_q.p, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(sep_words, d_s.p, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(d_in, ctx->stream);
-    cudaFreeAsync(d_q, ctx->stream);
-    cudaFreeAsync(d_s, ctx->stream);
     return CSVB200_OK;
 }
 
@@ -1559,17 +1760,15 @@ int csvb200_class_bytes(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, u
     if (!ctx || (n && (!host_bytes || !out))) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     if (n == 0) return CSVB200_OK;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    uint8_t *d_in = nullptr, *d_out = nullptr;
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_in, n, ctx->stream));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_out, n, ctx->stream));
-    int rc = upload(ctx, d_in, host_bytes, n);
+    DevBuf d_in, d_out;
+    CU_TRY(ctx, d_in.alloc(n, ctx->stream));
+    CU_TRY(ctx, d_out.alloc(n, ctx->stream));
+    int rc = upload(ctx, d_in.as<uint8_t>(), host_bytes, n);
     if (rc) return rc;
-    CU_TRY(ctx, launch_class_bytes(d_in, n, d_out, ctx->stream));
+    CU_TRY(ctx, launch_class_bytes(d_in.as<uint8_t>(), n, d_out.as<uint8_t>(), ctx->stream));
     ctx->launches += 1;
-    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(d_in, ctx->stream);
-    cudaFreeAsync(d_out, ctx->stream);
     return CSVB200_OK;
 }
 

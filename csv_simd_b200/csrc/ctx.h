@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/csvb200.h"
 #include "internal.h"
@@ -34,7 +35,10 @@ struct csvb200_ctx {
     size_t scratch_bytes = 0;
     uint64_t* d_cells = nullptr;
     uint64_t* h_cells = nullptr;
-    size_t next_cell = 0;
+    // ownership of the result cells: every live index object, shard job and running pipeline holds its cells
+    // until it is freed, so a lazily synced index can never read a cell that was handed to another operation
+    std::vector<uint8_t> cell_busy;   // [kRingCells]
+    size_t cell_hint = 0;
     // pinned rings of the streaming ingest (stream.cu), kept across calls: page-locking 240 MiB costs ~0.1 s
     uint8_t* h_stream_in[3] = {nullptr, nullptr, nullptr};
     uint64_t* h_stream_out[3] = {nullptr, nullptr, nullptr};
@@ -50,10 +54,27 @@ struct csvb200_ctx {
     uint64_t launches = 0;
     int kernel_override = 0;  // 0 = auto, 1 = simple, 2 = tma (CSVB200_KERNEL)
     uint32_t tune = 0;        // CSVB200_TUNE experiment knob
+    const uint8_t* dbg_desc_src = nullptr;   // (debug) input the look-back descriptors in d_scratch belong to
+    size_t dbg_desc_n = 0;
     bool host_result = true;  // kernels write {entries, end parity} straight into the pinned cell (CSVB200_HOST_RESULT=0: D2H copy node)
     bool e2e_ramp = true;     // host -> host pipeline starts with small chunks (CSVB200_E2E_RAMP=0: uniform chunks)
     size_t e2e_chunk = csvb200::kE2eChunk;   // granularity of the host -> host pipeline (CSVB200_E2E_CHUNK_MB)
     std::string err;
+};
+
+// cross-GPU exchange endpoint of one context (exchange.cu; protocol in internal.h ExchangeArgs)
+struct csvb200_exchange {
+    csvb200_ctx* ctx = nullptr;
+    uint32_t rank = 0, world = 1;
+    uint64_t epoch = 0;                                  // builds issued through this endpoint (collective order)
+    uint64_t* d_mbox = nullptr;                          // this rank's mailbox (cudaMalloc: IPC-exportable)
+    uint64_t* peer[csvb200::kExMaxWorld] = {};           // every rank's mailbox as mapped into this device
+    bool ipc_opened[csvb200::kExMaxWorld] = {};
+    uint64_t** d_peers = nullptr;                        // device copy of peer[]
+    bool connected = false;
+    uint64_t timeout_ns = 2000000000ull;                 // CSVB200_EXCHANGE_TIMEOUT_MS
+    uint64_t* d_row4 = nullptr;                          // {entries, end parity, carry used, total} of an end-to-end build
+    uint64_t* h_rows = nullptr;                          // pinned: one mailbox slot (host-side wait for all ranks)
 };
 
 struct csvb200_index {
@@ -77,7 +98,9 @@ struct csvb200_index {
     // speculative sharded build: carry cell {0, carry parity, decisive quote found, redo flag} (device / pinned mirror)
     bool speculative = false;
     bool verified = false;
-    size_t carry_cell = 0;
+    csvb200_exchange* ex = nullptr;         // built with the exchange inside the launch (csvb200_index_build_shard_exchange)
+    uint64_t ex_epoch = 0;
+    size_t carry_cell = SIZE_MAX;
     uint8_t* d_bytes_owned = nullptr;
     bool borrowed = false;                  // d_index belongs to the caller (csvb200_index_wrap_device): never freed here
     // Tape metadata (TapeCore::init)
@@ -90,12 +113,65 @@ struct csvb200_index {
 namespace csvb200 {
 
 int fail(csvb200_ctx* ctx, int code, const std::string& msg);
+// `count` consecutive free result cells (first-fit from a rotating hint); SIZE_MAX when the context holds
+// kRingCells live cells already
+size_t cell_alloc(csvb200_ctx* ctx, size_t count);
+void cell_release(csvb200_ctx* ctx, size_t first, size_t count);
+// cells held for the duration of one synchronous call
+struct CellLease {
+    csvb200_ctx* ctx;
+    size_t first, count;
+    CellLease(csvb200_ctx* c, size_t n) : ctx(c), first(cell_alloc(c, n)), count(n) {}
+    CellLease(const CellLease&) = delete;
+    CellLease& operator=(const CellLease&) = delete;
+    ~CellLease()
+    {
+        if (ok()) cell_release(ctx, first, count);
+    }
+    bool ok() const { return first != SIZE_MAX; }
+};
 int ensure_scratch(csvb200_ctx* ctx, size_t bytes);
 bool is_pinned(const void* p);
 SlicePool& io_pool(csvb200_ctx* ctx);   // the context's host-thread pool (CSVB200_IO_THREADS)
 // host -> device copy of n bytes on the context's stream; pinned sources go straight to cudaMemcpyAsync,
 // pageable ones through the context's pinned staging ring
 int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n);
+
+// stream-ordered device allocation released on scope exit (error paths included)
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t stream = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { reset(); }
+    cudaError_t alloc(size_t bytes, cudaStream_t s)
+    {
+        reset();
+        stream = s;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, s);
+    }
+    void reset()
+    {
+        if (p) cudaFreeAsync(p, stream);
+        p = nullptr;
+    }
+    void* release()
+    {
+        void* r = p;
+        p = nullptr;
+        return r;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+// device -> host copy of `count` index entries on the context's stream, synchronous; a pinned destination is DMA'd in
+// place, a pageable one goes through the context's two pinned bounce buffers and its host threads
+int download(csvb200_ctx* ctx, uint64_t* dst, const uint64_t* d_src, size_t count);
+int ensure_bounce(csvb200_ctx* ctx);
+// host-side wait for all ranks' rows of one build (exchange.cu)
+int exchange_wait_all(csvb200_exchange* ex, uint64_t epoch, uint64_t* counts, uint32_t* carries);
 
 #define CU_TRY(ctx, expr)                                                                       \
     do {                                                                                        \

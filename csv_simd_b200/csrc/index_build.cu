@@ -26,6 +26,8 @@
 //   5. ordered compaction: every thread expands its mask into 16-bit tile-relative
 //      offsets in shared memory at its scanned slot, then the CTA streams the tile's
 //      run out as full 16-byte stores (2 entries) of pos_bias + tile_base + offset.
+#include <mutex>
+
 #include "index_common.cuh"
 
 namespace csvb200 {
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
             }
             if (tile == 0u && p.write_sentinel && p.cap > 0) p.index[0] = 0ull;
             if (p.total_out != nullptr && (o0 | o1) != 0u) atomicAdd(p.total_out, (unsigned long long)(o0 + o1));
+            exchange_if_last(p);
         }
     }
     __syncthreads();
@@ -407,6 +410,11 @@ __global__ void verify_carry_kernel(const uint64_t* __restrict__ gathered, uint3
     }
 }
 
+__global__ void exchange_kernel(const ExchangeArgs ex, const uint64_t* __restrict__ row4)
+{
+    if (threadIdx.x == 0) exchange_post_and_resolve(ex, row4[0], row4[1], row4[2], row4[3]);
+}
+
 // ---- K1 known-answer exports --------------------------------------------------
 // quote_bits / all_struct words per 64-byte block, as get_struct_positions(16|3)
 // returns them (avx/stage1.rs:392,394); bytes past n read as zero.
@@ -443,12 +451,20 @@ __global__ void class_bytes_kernel(const uint8_t* __restrict__ in, uint64_t n, u
 cudaError_t launch_index_build(const BuildParams& p, cudaStream_t stream)
 {
     if (p.num_tiles == 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(index_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        configured = true;
+    // the opt-in to > 48 KiB of dynamic shared memory is per (kernel, device): cached per device ordinal
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[dev]) {
+            e = cudaFuncSetAttribute(index_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+            if (e != cudaSuccess) return e;
+            configured[dev] = true;
+        }
     }
     index_build_kernel<<<p.num_tiles, kThreads, sizeof(Smem), stream>>>(p);
     return cudaGetLastError();
@@ -478,6 +494,12 @@ cudaError_t launch_verify_carry(const uint64_t* gathered, uint32_t world, uint32
                                 uint64_t* final_out, cudaStream_t stream)
 {
     verify_carry_kernel<<<1, 32, 0, stream>>>(gathered, world, rank, cell, final_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exchange(const ExchangeArgs& ex, const uint64_t* row4, cudaStream_t stream)
+{
+    exchange_kernel<<<1, 32, 0, stream>>>(ex, row4);
     return cudaGetLastError();
 }
 

@@ -26,25 +26,63 @@
 //     (src/avx/stage1.rs:54-88) for free; the sub-row tail (< 128 B) is patched in by one thread.
 #include <cuda.h>
 
+#include <mutex>
+
 #include "index_common.cuh"
 
 namespace csvb200 {
 
 namespace {
 
-constexpr int kWorkerWarps = kWarps;             // 8
-constexpr int kProducerWarp = kWorkerWarps;      // warp 8
-constexpr int kLookbackWarp = kWorkerWarps + 1;  // warp 9
-constexpr int kTmaThreads = kThreads + 64;       // 320
-constexpr int kSub = 2;                          // sub-tiles (TMA boxes) per look-back descriptor
-constexpr int kSuperBytes = kSub * kTileBytes;   // 64 KiB per descriptor
-constexpr int kStages = 2;                       // TMA ring depth in sub-tiles (x 2 CTAs/SM = 128 KiB in flight per SM)
-constexpr int kStageCap = 8192;                  // entries per staging buffer; denser sub-tiles take extra rounds
-constexpr int kRowsPerTile = kTileBytes / 128;   // 256 = max TMA box extent
-constexpr int kSkew = 1;                         // super-tiles classified ahead of the one being compacted
-constexpr int kRing = kSkew + 1;                 // ring depth of the worker <-> look-back hand-off buffers
+constexpr int kBoxRows = 128;                    // rows of 128 B per TMA box (16 KiB)
 constexpr uint32_t kInvalidTile = 0xffffffffu;
 
+// Shape of one build of the kernel.  What differs between the shapes is how many CTAs fit on an SM
+// (the kernel is issue-bound on quote-heavy input, so resident warps matter) and how the shared memory that
+// buys them is found:
+//   kMinBlocks  CTAs per SM the register allocation is held to (__launch_bounds__)
+//   kStageBufs  staging buffers of the compaction: 2 = double buffered (one barrier per sub-tile),
+//               1 = a second barrier per sub-tile before the buffer is written again
+//   kStageCap   entries per staging buffer; denser sub-tiles take extra rounds
+//   kSub        sub-tiles (32 KiB TMA boxes) per look-back descriptor: the chain of prefixes advances a window
+//               of descriptors per L2 round trip, so bytes per descriptor set the chain's byte rate
+//   kSkew       super-tiles classified ahead of the one being compacted (what hides the look-back latency)
+//   kWorkers    worker warps per CTA (a sub-tile is kWorkers x 4 KiB; 16-bit staging offsets allow up to 16):
+//               the cost of the look-back chain grows with the number of CTAs in flight, so the same number
+//               of resident worker warps in fewer, larger CTAs shortens it
+template <int kMinBlocks_, int kStageBufs_, int kStageCap_, int kSub_, int kSkew_ = 1, int kWorkers_ = 8>
+struct TmaShape {
+    static constexpr int kWorkers = kWorkers_;
+    static constexpr int kWorkerThreads = kWorkers_ * 32;
+    static constexpr int kThreadsAll = kWorkerThreads + 64;    // + TMA producer warp + look-back warp
+    static constexpr int kProducerWarp = kWorkers_;
+    static constexpr int kLookbackWarp = kWorkers_ + 1;
+    static constexpr int kTile = kWorkerThreads * kBytesPerThread;   // bytes per sub-tile
+    static constexpr int kRows = kWorkerThreads;                      // 128-byte rows per sub-tile
+    static constexpr int kBoxes = kRows / kBoxRows;                   // TMA loads per sub-tile
+    static_assert(kWorkers_ % 4 == 0 && kWorkers_ <= 16, "sub-tiles are whole 16 KiB boxes and at most 64 KiB");
+    static constexpr int kSkew = kSkew_;
+    static constexpr int kRing = kSkew_ + 1;               // ring depth of the worker <-> look-back hand-off buffers
+    static constexpr int kMinBlocks = kMinBlocks_;
+    static constexpr int kStageBufs = kStageBufs_;
+    static constexpr int kStageCap = kStageCap_;
+    static constexpr int kSub = kSub_;
+    static constexpr int kSuperBytes = kSub_ * kTile;
+    static constexpr int kSlots = 2;                       // TMA ring depth in sub-tiles
+};
+using ShapeA = TmaShape<2, 2, 8192, 2>;   // 2 CTAs / SM, 99 KB each, 64 KiB per descriptor (round 1)
+using ShapeB = TmaShape<3, 1, 5120, 2>;   // 3 CTAs / SM, 75 KB each: one staging buffer
+using ShapeD = TmaShape<2, 2, 8192, 4>;   // 2 CTAs / SM, 128 KiB per descriptor
+using ShapeE = TmaShape<3, 1, 5120, 4>;   // 3 CTAs / SM, 128 KiB per descriptor
+using ShapeF = TmaShape<3, 1, 5120, 2, 2>;   // 3 CTAs / SM, two super-tiles of skew
+using ShapeG = TmaShape<2, 2, 8192, 2, 2>;   // 2 CTAs / SM, two super-tiles of skew
+using ShapeH = TmaShape<2, 1, 7680, 2, 1, 12>;   // 2 CTAs / SM x 12 worker warps: 48 KiB sub-tiles, 96 KiB per descriptor
+using ShapeI = TmaShape<1, 2, 12288, 2, 1, 16>;  // 1 CTA / SM x 16 worker warps: 64 KiB sub-tiles, 128 KiB per descriptor
+// (Tried and dropped: a ring of three 16 KiB half-stages shared by two warp groups, to fit double-buffered staging
+//  into 70 KB.  It is NOT sound: the groups alternate on a slot, one group can run a whole phase ahead of the other,
+//  and a parity wait cannot express that; it read stale data on the 1 GiB inputs.)
+
+template <int kSub, int kWorkerWarps>
 struct PrefixInfo {
     uint32_t pin[kSub];    // quote parity entering each sub-tile
     uint32_t cnt[kSub];    // entries each sub-tile emits (under its actual entry parity)
@@ -52,18 +90,23 @@ struct PrefixInfo {
     WarpState ws[kSub][kWorkerWarps];
 };
 
+template <class S>
 struct __align__(1024) SmemTma {
-    uint8_t in[kStages][kTileBytes];        // TMA destinations, 1024-byte aligned (SWIZZLE_128B)
-    uint16_t stage[2][kStageCap + 8];       // 16-bit sub-tile-relative offsets, double buffered
-    uint64_t full[kStages];                 // producer -> workers (TMA complete_tx)
-    uint64_t empty[kStages];                // workers -> producer
-    uint64_t agg_full[kRing];               // workers -> look-back warp
-    uint64_t pref_full[kRing];              // look-back warp -> workers
-    uint32_t tile_id[kStages];              // super-tile id of the sub-tile in each stage
-    uint32_t agg_tile[kRing];
-    uint32_t warp_agg[kRing][kSub][kWorkerWarps];
-    PrefixInfo pref[kRing];
+    uint8_t in[S::kSlots][S::kTile];                 // TMA destinations, 1024-byte aligned (SWIZZLE_128B)
+    uint16_t stage[S::kStageBufs][S::kStageCap + 8];   // 16-bit sub-tile-relative offsets
+    uint64_t full[S::kSlots];               // producer -> workers (TMA complete_tx)
+    uint64_t empty[S::kSlots];              // workers -> producer
+    uint64_t agg_full[S::kRing];               // workers -> look-back warp
+    uint64_t pref_full[S::kRing];              // look-back warp -> workers
+    uint32_t tile_id[S::kSlots];            // super-tile id of the part in each slot
+    uint32_t agg_tile[S::kRing];
+    uint32_t warp_agg[S::kRing][S::kSub][S::kWorkers];
+    PrefixInfo<S::kSub, S::kWorkers> pref[S::kRing];
 };
+
+// three CTAs per SM: 3 x (dynamic + 1 KiB reserved per CTA) must fit the SM's 228 KiB
+static_assert(sizeof(SmemTma<ShapeB>) <= 75 * 1024 && sizeof(SmemTma<ShapeF>) <= 75 * 1024, "3 CTAs / SM need <= 75 KiB each");
+static_assert(sizeof(SmemTma<ShapeH>) <= 113 * 1024, "2 CTAs / SM need <= 113 KiB each");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,10 +145,12 @@ __device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap*
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+template <class S>
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(S::kWorkerThreads) : "memory"); }
 
 // streams staged entries [j0, j1) (staging indices, j0 even) of a run whose staging index 0 maps to
 // global slot gbase; positions are tile_pos + 16-bit offset
+template <class S>
 __device__ __forceinline__ void copy_out_range(const BuildParams& p, const uint16_t* stg, uint32_t local0, uint32_t j0,
                                                uint32_t j1, uint64_t gbase, uint64_t tile_pos, uint32_t tid)
 {
@@ -115,13 +160,13 @@ __device__ __forceinline__ void copy_out_range(const BuildParams& p, const uint1
         // (Splitting tile_pos into a shared high word and one 32-bit add per entry halves this loop's instructions
         //  (11 -> 5 per store) and measured SLOWER twice, 0.416 vs 0.400 ms: the stores then leave in bursts that
         //  collide with the TMA reads; the paced version interleaves better with them.)
-        for (uint32_t j = j0 + 2u * tid; j < j1e; j += 2u * kThreads) {
+        for (uint32_t j = j0 + 2u * tid; j < j1e; j += 2u * S::kWorkerThreads) {
             const uint32_t pr = *reinterpret_cast<const uint32_t*>(&stg[j - local0]);
             stg_128(out + j, tile_pos + (pr & 0xffffu), tile_pos + (pr >> 16));
         }
         if ((j1 & 1u) && tid == 0 && j1 > j0) out[j1 - 1] = tile_pos + stg[j1 - 1 - local0];
     } else {
-        for (uint32_t j = j0 + tid; j < j1; j += kThreads)
+        for (uint32_t j = j0 + tid; j < j1; j += S::kWorkerThreads)
             if (gbase + j < p.cap) out[j] = tile_pos + stg[j - local0];
     }
 }
@@ -132,6 +177,7 @@ struct TileRegs {
     uint32_t x[kGroups];   // in-string masks relative to the warp start
     uint32_t exc;          // packed exclusive warp scan: entries before this thread (outside-hypothesis | total << 16)
 };
+template <int kSub>
 struct SuperRegs {
     TileRegs sub[kSub];
     uint32_t tile;         // super-tile id
@@ -139,110 +185,105 @@ struct SuperRegs {
 
 // Ordered compaction of one sub-tile: expand the masks into 16-bit offsets in shared memory at the
 // scanned slots, then stream the run out as 16-byte stores.  `seq` numbers the sub-tile compactions
-// of this CTA (it alternates the staging buffer).
-__device__ __forceinline__ void compact_sub(SmemTma& sm, const BuildParams& p, const TileRegs& t, const PrefixInfo& pi,
+// of this CTA (it alternates the staging buffer when there are two).
+template <class S>
+__device__ __forceinline__ void compact_sub(SmemTma<S>& sm, const BuildParams& p, const TileRegs& t, const PrefixInfo<S::kSub, S::kWorkers>& pi,
                                             int sub, uint32_t super_tile, uint32_t seq, uint32_t tid, uint32_t warp)
 {
+    constexpr uint32_t kCap = (uint32_t)S::kStageCap;
     const uint32_t pin = pi.pin[sub];
     const uint32_t cnt = pi.cnt[sub];
     const uint64_t g0 = p.out_base + pi.base[sub];   // slot of the sub-tile's first entry
     const uint32_t head = (uint32_t)(g0 & 1ull);      // keep even slots on even staging indices
     const uint32_t end = cnt + head;
     const uint64_t gbase = g0 - head;
-    const uint64_t tile_pos = p.pos_bias + (uint64_t)super_tile * kSuperBytes + (uint64_t)sub * kTileBytes;
+    const uint64_t tile_pos = p.pos_bias + (uint64_t)super_tile * S::kSuperBytes + (uint64_t)sub * S::kTile;
     const WarpState ws = pi.ws[sub][warp];
     const uint32_t h = pin ^ ws.par;                  // parity entering this warp
     const uint32_t ex_a0 = t.exc & 0xffffu, ex_tt = t.exc >> 16;
     const uint32_t slot0 = head + (pin ? ws.off1 : ws.off0) + (h ? ex_tt - ex_a0 : ex_a0);
     const uint32_t flip = 0u - h;
-    uint16_t* stg = sm.stage[seq & 1u];
-    if (end <= (uint32_t)kStageCap) {
+    uint16_t* stg = sm.stage[S::kStageBufs == 2 ? (seq & 1u) : 0u];
+    // one staging buffer: the copy-out of the previous sub-tile must be over before it is written again
+    // (with two buffers the other buffer's barrier already orders this)
+    if (S::kStageBufs == 1) worker_barrier<S>();
+    if (end <= kCap) {
         uint16_t* dst = stg + slot0;
-        if (!(p.tune & 64u)) {
-#pragma unroll
-            for (int g = 0; g < kGroups; ++g) {
-                uint32_t m = t.s[g] & ~(t.x[g] ^ flip);   // structure = all_struct & !string_mask (avx/stage1.rs:400-406)
-                const uint32_t rel0 = tid * kBytesPerThread + 32u * g;
-                const uint32_t c = (uint32_t)__popc(m);
-                // two entries per trip: immediate store offsets, one pointer bump, half the branches
-                // (0.396 vs 0.403 ms on cfg2 against the one-entry loop kept below for A/B: CSVB200_TUNE=64;
-                //  walking two groups per loop for more ILP measured slower, 0.439 ms: this phase is issue-bound)
-#pragma unroll 1
-                for (uint32_t k = 0; k + 1u < c; k += 2u) {
-                    const uint32_t b0 = (uint32_t)__ffs((int)m) - 1u;
-                    m &= m - 1u;
-                    const uint32_t b1 = (uint32_t)__ffs((int)m) - 1u;
-                    m &= m - 1u;
-                    dst[0] = (uint16_t)(rel0 + b0);
-                    dst[1] = (uint16_t)(rel0 + b1);
-                    dst += 2;
-                }
-                if (c & 1u) *dst++ = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
-            }
-        } else {
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) {
             uint32_t m = t.s[g] & ~(t.x[g] ^ flip);   // structure = all_struct & !string_mask (avx/stage1.rs:400-406)
             const uint32_t rel0 = tid * kBytesPerThread + 32u * g;
-            while (m) {
-                *dst++ = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
-                m &= m - 1u;  // blsr (stage1.rs:239)
+            const uint32_t c = (uint32_t)__popc(m);
+            // two entries per trip: immediate store offsets, one pointer bump, half the branches
+            // (0.396 vs 0.403 ms on cfg2 against a one-entry loop; walking two groups per loop for more ILP
+            //  measured slower, 0.439 ms: this phase is issue-bound)
+#pragma unroll 1
+            for (uint32_t k = 0; k + 1u < c; k += 2u) {
+                const uint32_t b0 = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;   // blsr (stage1.rs:239)
+                const uint32_t b1 = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                dst[0] = (uint16_t)(rel0 + b0);
+                dst[1] = (uint16_t)(rel0 + b1);
+                dst += 2;
             }
+            if (c & 1u) *dst++ = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
         }
-        }
-        worker_barrier();
+        worker_barrier<S>();
         if (head && tid == 0 && cnt > 0 && g0 < p.cap) p.index[g0] = tile_pos + stg[1];
-        copy_out_range(p, stg, 0u, 2u * head, end, gbase, tile_pos, tid);
-        // no trailing barrier: this staging buffer is next written two compactions from now,
-        // behind the other buffer's worker_barrier()
+        copy_out_range<S>(p, stg, 0u, 2u * head, end, gbase, tile_pos, tid);
+        // no trailing barrier: see above
     } else {
         // dense sub-tile (more than kStageCap entries): several staging rounds
-        for (uint32_t r0 = 0; r0 < end; r0 += (uint32_t)kStageCap) {
+        for (uint32_t r0 = 0; r0 < end; r0 += kCap) {
             uint32_t slot = slot0;
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
                 uint32_t m = t.s[g] & ~(t.x[g] ^ flip);
                 const uint32_t rel0 = tid * kBytesPerThread + 32u * g;
                 while (m) {
-                    if (slot - r0 < (uint32_t)kStageCap) stg[slot - r0] = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
+                    if (slot - r0 < kCap) stg[slot - r0] = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
                     ++slot;
                     m &= m - 1u;
                 }
             }
-            worker_barrier();
-            const uint32_t r1 = min(end, r0 + (uint32_t)kStageCap);
+            worker_barrier<S>();
+            const uint32_t r1 = min(end, r0 + kCap);
             if (r0 == 0 && head && tid == 0 && cnt > 0 && g0 < p.cap) p.index[g0] = tile_pos + stg[1];
-            copy_out_range(p, stg, r0, r0 == 0 ? 2u * head : r0, r1, gbase, tile_pos, tid);
-            worker_barrier();
+            copy_out_range<S>(p, stg, r0, r0 == 0 ? 2u * head : r0, r1, gbase, tile_pos, tid);
+            worker_barrier<S>();
         }
     }
 }
 
 // compaction of the `it`-th super-tile this CTA processed
-__device__ __forceinline__ void compact_super(SmemTma& sm, const BuildParams& p, const SuperRegs& t, uint32_t it,
+template <class S>
+__device__ __forceinline__ void compact_super(SmemTma<S>& sm, const BuildParams& p, const SuperRegs<S::kSub>& t, uint32_t it,
                                               uint32_t tid, uint32_t warp)
 {
-    const uint32_t pb = it % kRing;
-    mbar_wait(&sm.pref_full[pb], (it / kRing) & 1u);
-    const PrefixInfo& pi = sm.pref[pb];
+    const uint32_t pb = it % S::kRing;
+    mbar_wait(&sm.pref_full[pb], (it / S::kRing) & 1u);
+    const PrefixInfo<S::kSub, S::kWorkers>& pi = sm.pref[pb];
 #pragma unroll
-    for (int sub = 0; sub < kSub; ++sub) compact_sub(sm, p, t.sub[sub], pi, sub, t.tile, it * kSub + sub, tid, warp);
+    for (int sub = 0; sub < S::kSub; ++sub) compact_sub<S>(sm, p, t.sub[sub], pi, sub, t.tile, it * S::kSub + sub, tid, warp);
 }
 
-__global__ void __launch_bounds__(kTmaThreads, 2)
+template <class S>
+__global__ void __launch_bounds__(S::kThreadsAll, S::kMinBlocks)
 index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    SmemTma& sm = *reinterpret_cast<SmemTma*>(smem_raw);
+    SmemTma<S>& sm = *reinterpret_cast<SmemTma<S>*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
+    constexpr int kSub = S::kSub, kSkew = S::kSkew, kRing = S::kRing, kWorkerWarps = S::kWorkers;
 
     if (p.run_flag != nullptr && *p.run_flag == 0u) return;   // conditional redo that is not needed
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < S::kSlots; ++i) {
             mbar_init(&sm.full[i], 1);
             mbar_init(&sm.empty[i], kWorkerWarps);
         }
@@ -255,7 +296,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
     }
     __syncthreads();
 
-    if (warp == kProducerWarp) {
+    if (warp == S::kProducerWarp) {
         // ===== TMA producer: one elected lane =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
@@ -268,21 +309,23 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 if (tile >= p.num_tiles) tile = kInvalidTile;
 #pragma unroll
                 for (int sub = 0; sub < kSub; ++sub) {
-                    const uint32_t sc = it * kSub + sub, st = sc % kStages;
-                    mbar_wait(&sm.empty[st], ((sc / kStages) & 1u) ^ 1u);
+                    const uint32_t sc = it * kSub + sub, st = sc % S::kSlots;
+                    mbar_wait(&sm.empty[st], ((sc / S::kSlots) & 1u) ^ 1u);
                     sm.tile_id[st] = tile;
                     if (tile == kInvalidTile) {
                         mbar_arrive(&sm.full[st]);
-                        break;
+                        break;   // the workers stop after an invalid sub-tile 0
                     }
-                    mbar_arrive_expect_tx(&sm.full[st], (uint32_t)kTileBytes);
-                    tma_load_tile(sm.in[st], &tmap, 0, (int32_t)((tile * (uint32_t)kSub + sub) * (uint32_t)kRowsPerTile),
-                                  &sm.full[st]);
+                    mbar_arrive_expect_tx(&sm.full[st], (uint32_t)S::kTile);
+#pragma unroll
+                    for (int bx = 0; bx < S::kBoxes; ++bx)
+                        tma_load_tile(sm.in[st] + bx * (kBoxRows * 128), &tmap, 0,
+                                      (int32_t)((tile * (uint32_t)kSub + sub) * (uint32_t)S::kRows + bx * kBoxRows), &sm.full[st]);
                 }
                 if (tile == kInvalidTile) break;
             }
         }
-    } else if (warp == kLookbackWarp) {
+    } else if (warp == S::kLookbackWarp) {
         // ===== scan of warp aggregates + decoupled look-back =====
         uint64_t cta_total = 0ull;   // separators (inside + outside quotes) of this CTA's super-tiles (lane 0)
         for (uint32_t it = 0;; ++it) {
@@ -290,7 +333,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             mbar_wait(&sm.agg_full[b], (it / kRing) & 1u);
             const uint32_t tile = sm.agg_tile[b];
             if (tile == kInvalidTile) break;
-            PrefixInfo& pi = sm.pref[b];
+            PrefixInfo<kSub, kWorkerWarps>& pi = sm.pref[b];
             // fold the kSub x 8 warp aggregates in file order; remember the state entering every warp
             // and the (parity, c0, c1) composite at every sub-tile boundary
             uint32_t par = 0u, o0 = 0u, o1 = 0u;
@@ -320,10 +363,9 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                                kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
             uint32_t pin;
             uint64_t base;
-            if (p.tune == 2)
-                decoupled_lookback<2>(p, tile, lane, pin, base);
-            else
-                decoupled_lookback<1>(p, tile, lane, pin, base);   // measured best: 0.45 / 0.48 / 0.59 ms for 1 / 2 / 4
+            // one 32-descriptor window per round trip (wider windows measured slower both rounds: 0.400 / 0.427 ms
+            // for 64 / 128 on cfg2 against 0.395 -- more polling traffic on the same lines)
+            decoupled_lookback<1>(p, tile, lane, pin, base);
             if (lane == 0) {
                 const uint32_t pend = pin ^ par;
                 const uint64_t cend = base + (pin ? o1 : o0);
@@ -345,19 +387,22 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             }
             __syncwarp();
         }
-        if (lane == 0 && p.total_out != nullptr && cta_total != 0ull) atomicAdd(p.total_out, (unsigned long long)cta_total);
+        if (lane == 0) {
+            if (p.total_out != nullptr && cta_total != 0ull) atomicAdd(p.total_out, (unsigned long long)cta_total);
+            exchange_if_last(p);
+        }
     } else {
         // ===== workers =====
         const uint64_t full_rows = p.n >> 7;
         const uint32_t tail = (uint32_t)(p.n & 127u);
         // masks of the super-tiles that are classified but not yet compacted (kSkew of them, oldest first)
-        SuperRegs pend[kSkew];
+        SuperRegs<kSub> pend[kSkew];
 #pragma unroll
         for (int k = 0; k < kSkew; ++k) pend[k].tile = kInvalidTile;
 
         for (uint32_t it = 0;; ++it) {
             const uint32_t b = it % kRing;
-            SuperRegs cur;
+            SuperRegs<kSub> cur;
             cur.tile = kInvalidTile;
 #pragma unroll
             for (int sub = 0; sub < kSub; ++sub) {
@@ -366,15 +411,15 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) tr.s[g] = tr.x[g] = 0u;
                 if (sub > 0 && cur.tile == kInvalidTile) continue;   // the producer stops after an invalid sub-tile 0
-                const uint32_t sc = it * kSub + sub, st = sc % kStages;
-                mbar_wait(&sm.full[st], (sc / kStages) & 1u);
+                const uint32_t sc = it * kSub + sub, st = sc % S::kSlots;
+                mbar_wait(&sm.full[st], (sc / S::kSlots) & 1u);
                 const uint32_t tile = sm.tile_id[st];
                 cur.tile = tile;
                 if (tile == kInvalidTile) continue;
 
                 uint8_t* in = sm.in[st];
                 // the sub-row tail of the file is outside the tensor map: its owner patches it in
-                if (tail != 0u && ((uint64_t)tile * kSub + sub) * kRowsPerTile + tid == full_rows) {
+                if (tail != 0u && ((uint64_t)tile * kSub + sub) * S::kRows + tid == full_rows) {
                     for (uint32_t k = 0; k < tail; ++k) {
                         const uint32_t c = (uint32_t)kChunks * tid + (k >> 4);
                         in[16u * (c ^ ((c >> 3) & 7u)) + (k & 15u)] = p.in[full_rows * 128u + k];
@@ -399,7 +444,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                     tr.s[g] = m.sep;
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty[st]);  // stage can be refilled
+                if (lane == 0) mbar_arrive(&sm.empty[st]);  // slot can be refilled
 
                 // ---- quote regions relative to the warp start (string_mask, avx/stage1.rs:397) ----
                 uint32_t warp_par = 0u, anyq = 0u;
@@ -442,12 +487,12 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
 
             // ---- ordered compaction of the super-tile classified kSkew iterations ago: its look-back has
             //      had kSkew classify phases to complete ----
-            if (pend[0].tile != kInvalidTile) compact_super(sm, p, pend[0], it - kSkew, tid, warp);
+            if (pend[0].tile != kInvalidTile) compact_super<S>(sm, p, pend[0], it - kSkew, tid, warp);
             if (cur.tile == kInvalidTile) {
                 // drain: the younger pending super-tiles, oldest first
 #pragma unroll
                 for (int k = 1; k < kSkew; ++k)
-                    if (pend[k].tile != kInvalidTile) compact_super(sm, p, pend[k], it - kSkew + k, tid, warp);
+                    if (pend[k].tile != kInvalidTile) compact_super<S>(sm, p, pend[k], it - kSkew + k, tid, warp);
                 break;
             }
 #pragma unroll
@@ -476,12 +521,24 @@ EncodeTiledFn encode_tiled_fn()
 
 }  // namespace
 
-bool tma_path_usable(uint64_t n) { return n >= 4ull * kSuperBytes && encode_tiled_fn() != nullptr; }
+bool tma_path_usable(uint64_t n) { return n >= 8ull * kTileBytes && encode_tiled_fn() != nullptr; }
 
-cudaError_t launch_index_build_tma(const BuildParams& p_in, cudaStream_t stream)
+namespace {
+
+// cudaFuncSetAttribute and the occupancy are properties of (kernel, device): cached per device ordinal
+// (a second context on another GPU of the same process needs its own opt-in to > 48 KiB of shared memory)
+constexpr int kMaxDevices = 64;
+struct ShapeState {
+    std::mutex mu;
+    int grid_cap[kMaxDevices] = {};
+};
+
+template <class S>
+cudaError_t launch_shape(const BuildParams& p_in, cudaStream_t stream)
 {
+    static ShapeState state;
     BuildParams p = p_in;
-    p.num_tiles = (uint32_t)((p.n + kSuperBytes - 1) / kSuperBytes);   // descriptors are per super-tile here
+    p.num_tiles = (uint32_t)((p.n + S::kSuperBytes - 1) / S::kSuperBytes);   // descriptors are per super-tile here
     if (p.num_tiles == 0) p.num_tiles = 1;
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return cudaErrorNotSupported;
@@ -489,28 +546,56 @@ cudaError_t launch_index_build_tma(const BuildParams& p_in, cudaStream_t stream)
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {128, (cuuint64_t)(p.n >> 7)};
     const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {128, (cuuint32_t)kRowsPerTile};
+    const cuuint32_t box[2] = {128, (cuuint32_t)kBoxRows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(p.in), gdim, gstride, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);   // (promotion NONE: no difference)
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    static int grid_cap = 0;
-    if (grid_cap == 0) {
-        cudaError_t e = cudaFuncSetAttribute(index_build_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(SmemTma));
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 148, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, index_build_tma_kernel, kTmaThreads, sizeof(SmemTma));
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        grid_cap = sms * per_sm;   // persistent: one resident CTA per slot (2 per SM by design)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    int grid_cap;
+    {
+        std::lock_guard<std::mutex> lock(state.mu);
+        if (state.grid_cap[dev] == 0) {
+            e = cudaFuncSetAttribute(index_build_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(SmemTma<S>));
+            if (e != cudaSuccess) return e;
+            cudaFuncSetAttribute(index_build_tma_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+            int sms = 148, per_sm = 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, index_build_tma_kernel<S>, S::kThreadsAll,
+                                                              sizeof(SmemTma<S>));
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+            state.grid_cap[dev] = sms * per_sm;   // persistent: one resident CTA per slot
+        }
+        grid_cap = state.grid_cap[dev];
     }
-    unsigned grid = (unsigned)(p.num_tiles < (uint32_t)grid_cap ? p.num_tiles : (uint32_t)grid_cap);
-    index_build_tma_kernel<<<grid, kTmaThreads, sizeof(SmemTma), stream>>>(p, tmap);
+    const unsigned grid = (unsigned)(p.num_tiles < (uint32_t)grid_cap ? p.num_tiles : (uint32_t)grid_cap);
+    index_build_tma_kernel<S><<<grid, S::kThreadsAll, sizeof(SmemTma<S>), stream>>>(p, tmap);
     return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream)
+{
+    // CSVB200_TUNE bits 12-14 force a shape (A/B of the shapes on the same box); 0 = the default
+    switch ((p.tune >> 12) & 15u) {
+    case 1: return launch_shape<ShapeA>(p, stream);
+    case 2: return launch_shape<ShapeB>(p, stream);
+    case 3: return launch_shape<ShapeD>(p, stream);
+    case 4: return launch_shape<ShapeE>(p, stream);
+    case 5: return launch_shape<ShapeF>(p, stream);
+    case 6: return launch_shape<ShapeG>(p, stream);
+    case 7: return launch_shape<ShapeH>(p, stream);
+    case 8: return launch_shape<ShapeI>(p, stream);
+    default: return launch_shape<ShapeB>(p, stream);   // r02: 0.391 / 0.342 ms on cfg2 / cfg3 against 0.395 / 0.346 for A
+    }
 }
 
 }  // namespace csvb200

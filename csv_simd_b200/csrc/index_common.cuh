@@ -30,6 +30,82 @@ __device__ __forceinline__ void stg_128(void* p, uint64_t a, uint64_t b)
     asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One thread.  Posts this shard's row {entries under the carry it used, end parity, carry used, total separators}
+// to (slot = epoch % kExRing, row = rank) of EVERY rank's mailbox over peer-mapped pointers, then waits on its OWN
+// mailbox for the rows of the lower ranks and derives from them (exactly what verify_carry_kernel derives from an
+// all-gathered array): the true carry-in parity of this shard (XOR of the lower shards' parities, parity = end ^ used),
+// the entries the lower shards emit under THEIR true carries (flipping a carry swaps inside / outside separators, so
+// the other count is total - entries), and whether this shard's guess was wrong.
+static __device__ __noinline__ void exchange_post_and_resolve(const ExchangeArgs& ex, uint64_t entries, uint64_t end_parity,
+                                                       uint64_t used, uint64_t total)
+{
+    const uint64_t off = ((ex.epoch % kExRing) * kExMaxWorld) * kExRowWords;
+    for (uint32_t r = 0; r < ex.world; ++r) {
+        uint64_t* row = ex.peers[r] + off + (uint64_t)ex.rank * kExRowWords;
+        row[0] = entries;
+        row[1] = end_parity;
+        row[2] = used;
+        row[3] = total;
+    }
+    __threadfence_system();
+    for (uint32_t r = 0; r < ex.world; ++r)
+        st_release_sys_u64(ex.peers[r] + off + (uint64_t)ex.rank * kExRowWords + 4, ex.epoch);
+    const uint64_t* mine = ex.peers[ex.rank] + off;
+    const uint64_t t0 = global_timer_ns();
+    uint64_t carry = 0ull, below = 0ull, err = 0ull;
+    for (uint32_t j = 0; j < ex.rank && !err; ++j) {
+        const uint64_t* row = mine + (uint64_t)j * kExRowWords;
+        uint64_t e;
+        while ((e = ld_acquire_sys_u64(row + 4)) != ex.epoch) {
+            // a LARGER epoch: the writer lapped the ring (more than kExRing builds ahead of this rank)
+            if (e > ex.epoch || global_timer_ns() - t0 > ex.timeout_ns) {
+                err = 1ull;
+                break;
+            }
+            __nanosleep(100);
+        }
+        if (err) break;
+        const uint64_t cnt = ld_volatile_u64(row + 0), tot = ld_volatile_u64(row + 3);
+        const uint64_t us = ld_volatile_u64(row + 2) & 1ull, en = ld_volatile_u64(row + 1) & 1ull;
+        below += carry == us ? cnt : tot - cnt;
+        carry ^= en ^ us;
+    }
+    const uint64_t redo = (!err && carry != (used & 1ull)) ? 1ull : 0ull;
+    ex.out[0] = 0ull;
+    ex.out[1] = carry;
+    ex.out[2] = below | (err << 63);
+    ex.out[3] = redo;
+    if (ex.out_host != nullptr) {
+        ex.out_host[0] = 0ull;
+        ex.out_host[1] = carry;
+        ex.out_host[2] = below | (err << 63);
+        ex.out_host[3] = redo;
+    }
+}
+
 struct WarpState {
     uint32_t par;   // quote parity of the warps before this one (relative to tile start)
     uint32_t off0;  // entries emitted by those warps if the tile is entered outside quotes
@@ -70,6 +146,21 @@ __device__ __forceinline__ void write_result(const BuildParams& p, uint64_t cend
         p.result2[1] = pend;
         if (p.result2_words >= 3u) p.result2[2] = (virtual_prefix_desc(p) >> 61) & 1ull;
     }
+}
+
+// Called by one thread of every CTA when its look-back role is over (its separator total already added to
+// *p.total_out): the LAST such CTA of the launch holds the complete {entries, end parity} and total and runs the exchange
+// while other CTAs may still be compacting -- the NVLink round trip hides behind the tail of the launch.
+__device__ __forceinline__ void exchange_if_last(const BuildParams& p)
+{
+    if (p.ex.peers == nullptr) return;
+    __threadfence();
+    if (atomicAdd(p.ex_done, 1u) != gridDim.x - 1u) return;
+    __threadfence();
+    const uint64_t entries = ld_volatile_u64(p.result + 0), endp = ld_volatile_u64(p.result + 1);
+    const uint64_t total = p.total_out != nullptr ? ld_volatile_u64(reinterpret_cast<const uint64_t*>(p.total_out)) : 0ull;
+    const uint64_t used = (virtual_prefix_desc(p) >> 61) & 1ull;
+    exchange_post_and_resolve(p.ex, entries, endp, used, total);
 }
 
 // Warp-parallel decoupled look-back over the monoid (p, c0, c1) (see index_build.cu header).
@@ -130,7 +221,17 @@ __device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_
         const uint32_t ls = stopped ? (uint32_t)(__ffs(stopped) - 1) : 32u;   // nearest lane that stopped
         const uint32_t ls_stop = __shfl_sync(0xffffffffu, stop, (int)(ls & 31u));
         if (ls < 32u && ls_stop == 1u) {   // an unpublished tile lies before the nearest prefix: poll again
-            __nanosleep(64);
+            if (p.tune & 1u) {
+                // wait on THAT descriptor alone (one line instead of the whole window per poll: hundreds of look-back
+                // warps poll at the same time and their traffic competes with the data streams in L2), then rescan
+                const int64_t widx = idx0 - (int64_t)ls * kLookbackPerLane - (kLookbackPerLane - 1);
+                if (lane == 0 && widx >= 0) {
+                    while ((ld_relaxed_u64(p.desc + widx * kDescStride) >> 62) == 0ull) __nanosleep(32);
+                }
+                __syncwarp();
+            } else {
+                __nanosleep(64);
+            }
             continue;
         }
         // lanes 0..ls contribute (lane ls only the tiles nearer than its prefix)

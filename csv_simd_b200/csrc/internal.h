@@ -28,6 +28,29 @@ constexpr uint64_t kStatusPrefix = 2ull << 62;
 constexpr uint64_t kParityBit = 1ull << 61;
 constexpr uint64_t kCountMask = (1ull << 61) - 1;
 
+// ---- cross-GPU exchange over peer-mapped mailboxes (NVLink P2P stores; no collective library) ----------------
+// Every rank owns a mailbox in its own HBM: kExRing slots (one per build, epoch % kExRing) of kExMaxWorld rows of
+// 8 words {entries under the carry used, end parity, carry used, total separators, epoch, -, -, -}.  A rank POSTS its
+// row into the same (slot, row = its rank) of EVERY rank's mailbox (remote stores, then the epoch word after a
+// system-scope fence) and WAITS, on its own mailbox only, for the rows of the LOWER ranks: the true carry of shard k is
+// the XOR of the lower shards' parities and its base the sum of their true counts, so nothing above k is needed
+// before k can go on -- which also means ranks emulated one after another on one GPU never wait on a later launch.
+constexpr uint32_t kExRing = 1024;
+constexpr uint32_t kExMaxWorld = 16;
+constexpr uint32_t kExRowWords = 8;
+constexpr size_t kExMailboxBytes = (size_t)kExRing * kExMaxWorld * kExRowWords * sizeof(uint64_t);   // 1 MiB
+
+struct ExchangeArgs {
+    uint64_t* const* peers;  // device array [world]: every rank's mailbox as mapped into THIS device; null = no exchange
+    uint32_t rank, world;
+    uint64_t epoch;          // >= 1, the same on every rank for the same build
+    uint64_t timeout_ns;     // bound on the wait for the lower ranks' rows (a rank that never posts is an error, not a hang)
+    // out: {0, true carry-in parity, entries of the lower ranks | error << 63, redo flag} -- the carry cell the
+    // conditional redo launch reads -- and its pinned host mirror
+    uint64_t* out;
+    uint64_t* out_host;
+};
+
 struct BuildParams {
     const uint8_t* in;       // 16-byte aligned device pointer to the shard's bytes
     uint64_t n;              // bytes
@@ -59,6 +82,10 @@ struct BuildParams {
     // speculative multi-GPU build: when non-null the launch is a conditional redo and exits at once
     // unless *run_flag != 0 (the carry prediction turned out wrong)
     const uint32_t* run_flag;
+    // exchange inside the launch (multi-GPU, see ExchangeArgs): the last CTA to finish its look-back role posts this
+    // shard's row to every peer's mailbox and resolves the carry chain of the lower ranks
+    ExchangeArgs ex;
+    uint32_t* ex_done;       // CTAs whose look-back role is over; zeroed before launch (scratch)
 };
 
 // one tile per CTA, plain loads: small inputs and cross-check of the TMA kernel
@@ -78,6 +105,9 @@ cudaError_t launch_predict_carry(const uint8_t* in, uint64_t n, uint64_t window,
 // final_out[world][2] = {true entry count, true carry} of every rank
 cudaError_t launch_verify_carry(const uint64_t* gathered, uint32_t world, uint32_t rank, uint64_t* cell,
                                 uint64_t* final_out, cudaStream_t stream);
+// the exchange as a launch of its own (end-to-end pipelines, whose last chunk is not known in advance): posts
+// row4 = {entries, end parity, carry used, total separators} (device words) and resolves like the in-kernel form
+cudaError_t launch_exchange(const ExchangeArgs& ex, const uint64_t* row4, cudaStream_t stream);
 
 // debug / known-answer exports (K1): per 64-byte block quote and separator words, class bytes
 cudaError_t launch_block_masks(const uint8_t* in, uint64_t n, uint64_t* quote_words, uint64_t* sep_words,
@@ -99,9 +129,10 @@ struct LookupParams {
 };
 cudaError_t launch_seek(const LookupParams& p, cudaStream_t stream);
 
-// gather the bytes of resolved ranges into a packed buffer: out[out_off[i] .. out_off[i+1]) = bytes[start..end)
-cudaError_t launch_gather_bytes(const uint8_t* bytes, const uint64_t* ranges, const uint64_t* out_off, uint64_t nq,
-                                uint8_t* out, cudaStream_t stream);
+// gather the bytes of resolved ranges into a packed buffer: out[out_off[i] .. out_off[i+1]) = the input bytes
+// [start, end); ranges are GLOBAL positions, bytes[0] is global byte pos_bias and n bytes are addressable
+cudaError_t launch_gather_bytes(const uint8_t* bytes, uint64_t n, uint64_t pos_bias, const uint64_t* ranges,
+                                const uint64_t* out_off, uint64_t nq, uint8_t* out, cudaStream_t stream);
 cudaError_t launch_range_lengths(const uint64_t* ranges, uint64_t nq, uint64_t* lens, cudaStream_t stream);
 
 // K5 tape validation (tape.cu): first index slot whose separator class does not fit its place in the record

@@ -69,6 +69,7 @@ struct Pipeline {
             if (s.k_done) cudaEventDestroy(s.k_done);
             if (s.d_done) cudaEventDestroy(s.d_done);
         }
+        cell_release(ctx, cells0, kSlots + 1);
         cudaGetLastError();
     }
 
@@ -79,8 +80,8 @@ struct Pipeline {
         chunk = (chunk + 127) & ~size_t(127);          // chunk boundaries stay 128-byte aligned (TMA rows)
         out_cap = chunk / 2 + 4096;                    // entries per pinned output slot (4 x the chunk's bytes)
         CU_TRY(ctx, cudaSetDevice(ctx->device));
-        cells0 = ctx->next_cell + kSlots + 1 <= kRingCells ? ctx->next_cell : 0;
-        ctx->next_cell = (cells0 + kSlots + 1) % kRingCells;
+        cells0 = cell_alloc(ctx, kSlots + 1);   // held until the pipeline object dies
+        if (cells0 == SIZE_MAX) return fail(ctx, CSVB200_ERR_OOM, "no free result cells (4095 live index objects)");
         static_assert(kSlots == 3, "the context caches three ring slots");
         if (ctx->stream_chunk != chunk || ctx->stream_out_cap != out_cap) {   // (re)build the context's pinned rings
             for (int i = 0; i < kSlots; ++i) {

@@ -19,6 +19,12 @@ speculative protocol (default; one pass over the bytes and one exchange in the c
   verify   every rank: true carries = exclusive XOR-scan of (end ^ used); true counts from
            c0 + c1 = total; a shard whose guess was wrong (and only that shard) is re-indexed
 
+exchange protocol (round 2; pass exchange=make_exchange(ctx)): the same speculative scheme with the collective
+replaced by peer-mapped mailboxes -- every rank's 32-byte row is written straight into every peer's HBM over NVLink
+from inside the index-build launch, each rank resolves the carries of the LOWER ranks on the device, and the step is
+predictor + build launch + conditional re-index launch: no NCCL call, no verify launch, no host round trip
+(csvb200_index_build_shard_exchange).  torch.distributed is only used once, to hand the 64-byte IPC handles around.
+
 The index stays distributed: rank k holds entries [base_k, base_k + len_k) of the global index.
 No bulk data ever crosses GPUs.
 """
@@ -85,6 +91,19 @@ def verify_speculation(gathered: Sequence[Sequence[int]]):
     return carries, counts, redo
 
 
+def make_exchange(ctx: api.Context, group=None) -> api.Exchange:
+    """This rank's endpoint of the mailbox exchange, connected to every rank of `group` (processes of one node):
+    one all_gather of the 64-byte CUDA IPC handles at set-up time, nothing collective afterwards."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ex = ctx.exchange(rank, world)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, ex.handle(), group=group)
+        ex.connect(handles)
+        dist.barrier(group=group)     # every rank has mapped every mailbox before the first build posts
+    return ex
+
+
 @dataclass
 class ShardedIndex:
     local: api.StructureIndex   # this rank's segment (global byte positions)
@@ -96,7 +115,8 @@ class ShardedIndex:
 
 
 def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: int, group=None,
-                        resolve: bool = True, speculative: bool = True, predict_window: int = 0) -> ShardedIndex:
+                        resolve: bool = True, speculative: bool = True, predict_window: int = 0,
+                        exchange: Optional[api.Exchange] = None) -> ShardedIndex:
     """Index this rank's shard [global_offset, global_offset + n) of a file split across the ranks
     of `group` at arbitrary byte offsets.  Everything is stream-ordered on the current CUDA stream
     (which the Context must be bound to, see Context.set_stream); the host only synchronises once, at
@@ -115,6 +135,15 @@ def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: i
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     device = torch.device("cuda", ctx.device)
+    if exchange is not None:
+        # exchange=...: the whole step is ONE C call; the rows cross NVLink from inside the build launch
+        idx = ctx.index_build_shard_exchange(exchange, dev_ptr, n, global_offset, predict_window)
+        if not resolve:
+            return ShardedIndex(idx, -1, -1, -1, [])
+        info = idx.shard_info()                              # the only host sync: this rank's launches
+        counts, carries = exchange.counts(idx)               # host-side wait for the rows of ALL ranks
+        ps = [carries[k] ^ (carries[k + 1] if k + 1 < world else 0) for k in range(world)]   # informational
+        return ShardedIndex(idx, info["base"], sum(counts), info["carry_in"], ps, counts)
     if speculative:
         res_local = torch.empty(4, dtype=torch.int64, device=device)
         idx = ctx.index_build_shard_speculative(dev_ptr, n, rank, global_offset, emit_sentinel=(rank == 0),
@@ -157,7 +186,7 @@ def sharded_index_build(ctx: api.Context, dev_ptr: int, n: int, global_offset: i
 
 
 def sharded_index_build_to_host(ctx: api.Context, host_ptr: int, n: int, global_offset: int, dst_ptr: int, dst_cap: int,
-                                group=None):
+                                group=None, exchange: Optional[api.Exchange] = None):
     """End-to-end form: this rank's shard in (pinned) host memory -> this rank's index segment in host memory
     (csvb200_shard_build_to_host: chunked H2D, chained launches, overlapped D2H under the predicted carry), then
     the one all_gather and csvb200_shard_job_verify.  Returns (entries in dst, base slot of the segment in the
@@ -165,6 +194,10 @@ def sharded_index_build_to_host(ctx: api.Context, host_ptr: int, n: int, global_
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     device = torch.device("cuda", ctx.device)
+    if exchange is not None:
+        ln, info, counts = ctx.shard_build_to_host_exchange(exchange, host_ptr, n, global_offset, dst_ptr, dst_cap,
+                                                            want_counts=True)
+        return ln, info["base"], sum(counts), bool(info["redone"])
     res_local = torch.empty(4, dtype=torch.int64, device=device)
     _, job = ctx.shard_build_to_host(host_ptr, n, rank, global_offset, rank == 0, dst_ptr, dst_cap, res_local.data_ptr())
     res_all = torch.empty(4 * world, dtype=torch.int64, device=device)

@@ -52,6 +52,7 @@ _BY_CODE = {
     8: ReferencePanic,
     9: BufferError,
     10: ReferencePanic,
+    11: GpuError,
 }
 
 

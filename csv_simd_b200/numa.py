@@ -67,3 +67,34 @@ def bind_to_device(device: int) -> Optional[int]:
     except OSError:
         return None
     return node
+
+
+def why_unbound(device: int) -> str:
+    """One line saying why bind_to_device changed nothing on this host (recorded in the bench line)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        bus = getattr(p, "pci_bus_id", None)
+        if isinstance(bus, int):
+            bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    except Exception as e:  # noqa: BLE001
+        return f"no device properties: {e}"
+    bdf = str(bus).lower()
+    if len(bdf.split(":")[0]) == 8:
+        bdf = bdf[4:]
+    path = f"/sys/bus/pci/devices/{bdf}/numa_node"
+    try:
+        with open(path) as f:
+            raw = f.read().strip()
+    except OSError as e:
+        return f"{path}: {e.strerror or e}"
+    try:
+        nodes = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node"))
+    except OSError:
+        nodes = []
+    if int(raw) < 0:
+        return f"{path} = {raw} (the platform exposes no PCI -> NUMA topology; host nodes: {len(nodes)})"
+    cpus = set(node_cpus(int(raw))) & set(os.sched_getaffinity(0))
+    if not cpus:
+        return f"node {raw} has no CPU this process may run on (affinity {len(os.sched_getaffinity(0))} cpus)"
+    return "sched_setaffinity refused"

@@ -42,7 +42,8 @@ typedef enum csvb200_status {
     CSVB200_ERR_OOM = 7,
     CSVB200_ERR_INPUT_TOO_SMALL = 8,    /* n < 64: the reference panics (src/reader.rs:220-229, src/avx/stage1.rs:45-48) */
     CSVB200_ERR_CAPACITY = 9,
-    CSVB200_ERR_OUT_OF_BOUNDS = 10      /* a lookup slot past the index end: the reference panics on the Vec bounds check */
+    CSVB200_ERR_OUT_OF_BOUNDS = 10,     /* a lookup slot past the index end: the reference panics on the Vec bounds check */
+    CSVB200_ERR_EXCHANGE = 11           /* a peer GPU never posted its row (timeout) or lapped the mailbox ring */
 } csvb200_status;
 
 typedef struct csvb200_ctx csvb200_ctx;
@@ -183,6 +184,79 @@ int csvb200_shard_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
 int csvb200_shard_job_verify(csvb200_shard_job* job, const uint64_t* d_gathered, uint32_t world, uint64_t* d_final_out,
                              size_t* len_out, int* redone);
 void csvb200_shard_job_free(csvb200_shard_job* job);
+
+/* ---- the same protocol without a collective library: peer-mapped mailboxes over NVLink -----------------------
+ * (north_star: "one tiny allgather over NVLink exchanges those parity bits and counts"; README.md:24.)  Every rank
+ * owns a 1 MiB mailbox in its own HBM.  A build posts its 32-byte row {entries, end parity, carry used, separator
+ * total} into the same slot of EVERY rank's mailbox with plain remote stores from inside the index-build launch (the
+ * last CTA to finish does it, while others still compact), then waits -- on its own memory -- for the rows of the LOWER
+ * ranks only, derives its true carry-in, the entries before its segment and whether its guess was wrong, and leaves
+ * them where the conditional redo launch and the host find them.  No NCCL, no host round trip, no extra launch; a
+ * rank that never posts is reported as CSVB200_ERR_EXCHANGE after a timeout (CSVB200_EXCHANGE_TIMEOUT_MS, default
+ * 2000) instead of hanging the GPU.  Builds through an exchange are COLLECTIVE: every rank issues them in the same
+ * order.  At most 16 ranks; at most 1024 builds may be in flight ahead of the slowest rank (detected, not silent).
+ *
+ * Wiring: create one endpoint per context, hand every rank's 64-byte handle to every other rank by any means (the
+ * Python layer uses torch.distributed, a Rust caller its own channel) and connect.  Processes on one node map each
+ * other's mailboxes through CUDA IPC; contexts of ONE process (one per device) connect directly with peer access. */
+typedef struct csvb200_exchange csvb200_exchange;
+#define CSVB200_EXCHANGE_HANDLE_BYTES 64
+#define CSVB200_EXCHANGE_MAX_WORLD 16
+int csvb200_exchange_create(csvb200_ctx* ctx, uint32_t rank, uint32_t world, csvb200_exchange** out);
+int csvb200_exchange_handle(csvb200_exchange* ex, uint8_t out[CSVB200_EXCHANGE_HANDLE_BYTES]);
+/* handles = world x 64 bytes in rank order (this rank's own slot is ignored) */
+int csvb200_exchange_connect(csvb200_exchange* ex, const uint8_t* handles);
+/* all = the endpoints of every rank of this process, in rank order; connects every one of them */
+int csvb200_exchange_connect_local(csvb200_exchange* const* all, uint32_t world);
+void csvb200_exchange_destroy(csvb200_exchange* ex);
+
+/* Index this rank's device-resident shard [global_offset, global_offset + n): prediction, build, exchange and the
+ * conditional re-index are all enqueued on the context's stream; nothing waits on the host.  Rank 0 emits the
+ * sentinel.  predict_window as above. */
+int csvb200_index_build_shard_exchange(csvb200_ctx* ctx, csvb200_exchange* ex, const void* dev_bytes, size_t n,
+                                       uint64_t global_offset, uint64_t predict_window, csvb200_index** out);
+typedef struct csvb200_shard_info {
+    uint64_t base;      /* global slot of this rank's first entry (rank 0: 0, the sentinel) */
+    uint64_t entries;   /* entries in this rank's segment (rank 0 incl. the sentinel) */
+    uint64_t epoch;
+    uint32_t carry_in;  /* true quote parity entering the shard */
+    uint32_t redone;    /* the guess was wrong and the shard was re-indexed */
+    uint32_t rank, world;
+} csvb200_shard_info;
+/* synchronises with the build */
+int csvb200_index_shard_info(csvb200_index* idx, csvb200_shard_info* out);
+/* Waits (host side, bounded) until EVERY rank's row of that build has arrived and derives every rank's true entry
+ * count (rank 0 incl. the sentinel) and carry-in: counts[world], carries[world] (either may be NULL). */
+int csvb200_exchange_counts(csvb200_exchange* ex, csvb200_index* idx, uint64_t* counts, uint32_t* carries);
+
+/* End-to-end form: this rank's shard in HOST memory -> this rank's index segment in HOST memory (chunked uploads,
+ * chained launches, overlapped downloads under the predicted carry, exchange, re-index from the device copy only if
+ * the guess was wrong).  Synchronous.  counts / carries as above (optional: they make the call wait for all ranks). */
+int csvb200_shard_build_to_host_exchange(csvb200_ctx* ctx, csvb200_exchange* ex, const uint8_t* host_bytes, size_t n,
+                                         uint64_t global_offset, uint64_t* dst, size_t dst_cap, size_t* len_out,
+                                         csvb200_shard_info* info, uint64_t* counts, uint32_t* carries);
+
+/* ---- all GPUs of one process behind one call (what makes reader::read, src/reader.rs:150, drop-in at 8 GPUs:
+ * the caller of src/lib.rs:61-74 hands over ONE byte slice and gets ONE Vec<usize> back) ------------------------ */
+typedef struct csvb200_multi csvb200_multi;
+/* one context + exchange endpoint per listed device (a device may be listed twice: its shards then run one after
+ * another, which is how the protocol is exercised on a single GPU) */
+int csvb200_multi_create(const int* devices, int ndev, csvb200_multi** out);
+void csvb200_multi_destroy(csvb200_multi* m);
+const char* csvb200_multi_last_error(const csvb200_multi* m);
+int csvb200_multi_device_count(const csvb200_multi* m);
+/* Cuts host_bytes into ndev contiguous shards at arbitrary (unaligned) offsets -- cuts[ndev+1] if given, else
+ * k * n / ndev + 37 k + 13 -- uploads and indexes them concurrently (one host thread per device), exchanges carries
+ * and bases over peer memory, and writes ONE contiguous index into dst: exactly reader::read's output. */
+int csvb200_multi_index_build_to_host(csvb200_multi* m, const uint8_t* host_bytes, size_t n, const size_t* cuts,
+                                      uint64_t* dst, size_t dst_cap, size_t* len_out);
+typedef struct csvb200_multi_stats {
+    double seconds, upload_seconds, download_seconds;
+    uint64_t entries;
+    uint32_t redone_mask;     /* bit k: shard k was re-indexed */
+    uint32_t carry_mask;      /* bit k: shard k starts inside a quoted field */
+} csvb200_multi_stats;
+int csvb200_multi_last_stats(const csvb200_multi* m, csvb200_multi_stats* out);
 
 /* ---- index object: StructureIndex (src/stage1.rs:61) --------------------------------------- */
 /* Wrap `len` entries that already sit in device memory (e.g. the segments of a sharded build gathered

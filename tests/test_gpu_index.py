@@ -276,6 +276,10 @@ def test_full_size_properties(ctx, kind):
     assert E == cnt
     host = idx.to_host()
     assert int(host.sum(dtype=np.uint64)) == checksum
+    # element-wise, once per run: the whole 0.5-1.25 GB index against the oracle's index of the same bytes
+    want, _ = O.read_closed_form(data, 0, 0, with_sentinel=True)
+    assert want.size == E and np.array_equal(host, want)
+    del want
     assert host[0] == 0 and (np.diff(host[1:].astype(np.int64)) > 0).all()             # strictly sorted
     assert np.isin(data[host[1:]], np.array([0x2C, 0x0D, 0x0A], dtype=np.uint8)).all()  # entries are separators
     if kind == "cfg2_unquoted":
@@ -869,6 +873,29 @@ def test_beyond_4gib_positions(ctx):
     want = O.closed_form_numpy(win, 0, int(host[lo]), with_sentinel=False)
     assert (host[lo:k + 2001] == want).all()
     assert idx.tape_validate(256, False)["ok"] == 1
+    # BASELINE config 5 at full size on the same file: 10 M random (record, field) lookups + a 1 % tail of
+    # out-of-range probes, hit count and checksum of every (start, end) pair against the oracle's seek_field
+    rc, jump = idx.tape_init(256, False)
+    assert rc == rows + 1 and jump == 256
+    nq = 10_000_000
+    rec, fld = gen.queries(nq, rc, 256, seed=46)
+    tail = nq // 100
+    rec[-tail:-tail // 2] = rc - 1 + np.arange(tail - tail // 2, dtype=np.uint32)   # rec >= record_cnt - 1 -> None
+    fld[-tail // 2:] = 256 + np.arange(tail // 2, dtype=np.uint32) % 7               # fld >= field_cnt   -> None
+    d_rec = torch.from_numpy(rec.view(np.int32)).to(dev)
+    d_fld = torch.from_numpy(fld.view(np.int32)).to(dev)
+    d_out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+    idx.seek_fields_device(d_rec.data_ptr(), d_fld.data_ptr(), nq, d_out.data_ptr())
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint64)
+    cs_cpu, hits = O.seek_fields_timed(host, n, rc, 256, False, rec, fld)
+    live = got[:, 0] != np.uint64(U64MAX)
+    cs_gpu = int((got[live, 0] ^ (got[live, 1] << np.uint64(1))).sum(dtype=np.uint64))
+    assert hits == int(live.sum()) == nq - tail and cs_cpu == cs_gpu
+    assert not live[-tail:].any()
+    for i in range(0, nq - tail, nq // 64):   # and the bytes the ranges delimit
+        a, b = int(got[i, 0]), int(got[i, 1])
+        assert bytes(data[a:b]).isdigit() and data[a - 1] in (0x2C, 0x0A) and data[b] in (0x2C, 0x0A)
     idx.free()
 
 
@@ -936,3 +963,272 @@ def test_more_than_2_pow_32_entries(ctx):
         ctx.set_reserve(1, 3)
         del d
         torch.cuda.empty_cache()
+
+
+# ---- round 2: ownership of the result cells, shard-local gathers, a second device ------------------------------
+def test_result_cells_are_owned_until_free(ctx):
+    """More unsynced index objects than the context has result cells (4095): the build that cannot get a cell fails
+    loudly instead of aliasing a live one, every index still reports ITS length, and freeing makes room again."""
+    raw = [(b"a,b\n" + b"1,2\n" * (k % 7 + 1)) for k in range(16)]
+    raw = [r + b"x" * (64 - len(r) % 64) for r in raw]     # >= 64 bytes each
+    want = [O.closed_form_numpy(r).size for r in raw]
+    live = []
+    with pytest.raises(MemoryError) as ei:
+        for k in range(5000):
+            live.append((k % 16, ctx.index_build(raw[k % 16])))
+    assert "result cell" in str(ei.value) or "live index" in str(ei.value)
+    assert len(live) >= 4000
+    for j, idx in live[::97]:
+        assert len(idx) == want[j]
+    for _, idx in live:
+        idx.free()
+    again = ctx.index_build(raw[3])
+    assert len(again) == want[3]
+    again.free()
+
+
+def test_gather_fields_on_a_shard_with_global_offset(ctx):
+    """gather_fields must rebase the global (start, end) ranges by the shard's offset.  A shard that starts
+    at a row boundary is a CSV in its own right: its fields come back as bytes, identical to the oracle's slices."""
+    import torch
+    data, rows = gen.unquoted(1 << 20, seed=7)
+    raw = data.tobytes()
+    full = O.closed_form_numpy(raw)
+    cut = int(full[16 * 1000]) + 1              # first byte of row 1000 (16 separators per row)
+    assert cut % 16 != 0 or True
+    shard = np.frombuffer(raw[cut:], dtype=np.uint8)
+    dev = torch.device("cuda", ctx.device)
+    d = torch.zeros(shard.size + 64 + 16, dtype=torch.uint8, device=dev)
+    off = (-d.data_ptr()) % 16
+    d[off:off + shard.size].copy_(torch.from_numpy(shard.copy()))
+    # emit_sentinel so that the shard's own index starts with a sentinel entry; positions are GLOBAL (>= cut)
+    idx = ctx.index_build_shard_device(d.data_ptr() + off, shard.size, 0, cut, True)
+    host = idx.to_host()
+    assert host[0] == 0 and int(host[1]) > cut
+    rc, _ = idx.tape_init(16, False)
+    rec = np.array([0, 5, 17, rc - 2], dtype=np.uint32)
+    fld = np.array([1, 0, 15, 7], dtype=np.uint32)
+    offs, vals = idx.gather_fields(rec, fld)
+    rg = idx.seek_fields(rec, fld)
+    for i in range(rec.size):
+        a, b = int(rg[i, 0]), int(rg[i, 1])
+        assert a >= cut and bytes(vals[int(offs[i]):int(offs[i + 1])]) == raw[a:b] and raw[a:b].isdigit()
+    # field 0 of the shard's first row starts at the sentinel's position 0 + 1 = global byte 1: not in this shard
+    with pytest.raises(cs.errors.ReferencePanic):   # CSVB200_ERR_OUT_OF_BOUNDS
+        wrapped = ctx.index_wrap_device(idx.device_ptr, len(idx), shard.size, d.data_ptr() + off)
+        try:
+            wrapped.tape_init(16, False)
+            wrapped.gather_fields(np.array([0], dtype=np.uint32), np.array([1], dtype=np.uint32))
+        finally:
+            wrapped.free()
+    idx.free()
+
+
+def test_second_device_in_the_same_process():
+    """kernel attributes (> 48 KiB dynamic shared memory opt-in, occupancy) are per device.  A context on
+    device 1 of the same process must build the same index (both kernels)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    data, _ = gen.quoted(3 << 20, seed=9)
+    want = O.read_sse(data.tobytes())
+    for dev in (0, 1, 0):
+        c = cs.Context(dev)
+        for sl in (data, data[:100_000]):
+            idx = c.index_build(sl)
+            assert np.array_equal(idx.to_host(), O.read_sse(sl.tobytes()) if sl is not data else want)
+            idx.free()
+        c.close()
+
+
+def test_stream_read_callback_overrun_is_rejected(ctx):
+    """a read() that returns more than `cap` bytes is refused before anything is copied."""
+    def read(cap):
+        return b"x" * (cap + 1)
+    with pytest.raises(ValueError):
+        ctx.index_build_stream(read, lambda e, f: None, chunk_bytes=1 << 20)
+
+
+# ---- round 2: the exchange (peer-mapped mailboxes instead of a collective) and the single-process multi-GPU front end ----
+def _exchange_chain(ctxs, exs, raw, cuts, dev_of, window=0):
+    """Shards of `raw` through csvb200_index_build_shard_exchange, one rank after another IN RANK ORDER (a rank only
+    ever waits for lower ranks, so ranks that share one GPU may run sequentially).  Returns the concatenated index,
+    the shard infos and the per-rank counts / carries every rank's host view derives."""
+    import torch
+    G = len(cuts) - 1
+    keep, idxs, infos = [], [], []
+    for k in range(G):
+        lo, hi = cuts[k], cuts[k + 1]
+        buf = torch.zeros(max(hi - lo, 1) + 64, dtype=torch.uint8, device=dev_of(k))
+        if hi > lo:
+            buf[:hi - lo].copy_(torch.from_numpy(np.frombuffer(raw[lo:hi], dtype=np.uint8).copy()))
+        torch.cuda.synchronize(dev_of(k))
+        keep.append(buf)
+        idx = ctxs[k].index_build_shard_exchange(exs[k], buf.data_ptr(), hi - lo, lo, window)
+        infos.append(idx.shard_info())     # synchronises: rank k has posted before rank k + 1 starts
+        idxs.append(idx)
+    views = [exs[k].counts(idxs[k]) for k in range(G)]
+    got = np.concatenate([i.to_host() for i in idxs])
+    for i in idxs:
+        i.free()
+    return got, infos, views
+
+
+def _check_exchange_result(raw, cuts, got, infos, views):
+    want = O.closed_form_numpy(raw)
+    assert got.shape == want.shape and (got == want).all()
+    G = len(cuts) - 1
+    true_carry = [O.shard_summary(raw[:cuts[k]])[0] for k in range(G)]
+    seg = [O.closed_form_numpy(raw[cuts[k]:cuts[k + 1]], true_carry[k], cuts[k], with_sentinel=(k == 0)).size for k in range(G)]
+    assert [i["carry_in"] for i in infos] == true_carry
+    assert [i["entries"] for i in infos] == seg
+    assert [i["base"] for i in infos] == [sum(seg[:k]) for k in range(G)]
+    for counts, carries in views:          # every rank's host view of the whole exchange agrees with the oracle
+        assert counts == seg and carries == true_carry
+
+
+def test_exchange_emulated_ranks_on_one_gpu():
+    """The mailbox protocol with G ranks emulated by G contexts on ONE device (rank order): posts, waits on the lower
+    ranks, carry chain, bases, the misprediction re-index, the epochs of repeated builds; both kernels."""
+    import torch
+    dev = torch.device("cuda", 0)
+    for kname in ("tma", "simple"):
+        os.environ["CSVB200_KERNEL"] = kname
+        try:
+            G = 5
+            ctxs = [cs.Context(0) for _ in range(G)]
+            exs = [c.exchange(k, G) for k, c in enumerate(ctxs)]
+            cs.Exchange.connect_local(exs)
+            q, _ = gen.quoted(6 << 20, seed=44)
+            raw = q.tobytes()
+            n = len(raw)
+            cuts = [0] + [(k * n) // G + 37 * k + 13 for k in range(1, G)] + [n]
+            cuts[2] = raw.index(b'"', cuts[2]) + 1            # inside (or at the edge of) a quoted field
+            got, infos, views = _exchange_chain(ctxs, exs, raw, cuts, lambda k: dev)
+            _check_exchange_result(raw, cuts, got, infos, views)
+            assert 1 in [i["carry_in"] for i in infos] and not any(i["redone"] for i in infos)
+            # misleading data (an unescaped quote that looks like a closing one): that shard alone is re-indexed
+            raw2 = (b'aa,bb"\n,cc,dd\n' * 40000) + b'x,y\n'
+            cuts2 = [0, 14 * 10000 + 3, 14 * 20001 + 5, 14 * 30001 + 3, 14 * 35000, len(raw2)]
+            got, infos, views = _exchange_chain(ctxs, exs, raw2, cuts2, lambda k: dev)
+            _check_exchange_result(raw2, cuts2, got, infos, views)
+            assert any(i["redone"] for i in infos) and not infos[0]["redone"]
+            # forced boundaries (SURVEY 8d), empty and tiny shards, a third and fourth epoch on the same endpoints
+            body = b'id,"text, with ""escapes"" and\r\nnewlines",tail\r\n' * 4000
+            raw4 = b"h1,h2,h3\r\n" + body
+            inside, esc, crlf = raw4.index(b"text"), raw4.index(b'""') + 1, raw4.index(b"\r\n", 50) + 1
+            cuts4 = [0, inside, esc, crlf, len(raw4) // 2 + 5, len(raw4)]
+            got, infos, views = _exchange_chain(ctxs, exs, raw4, cuts4, lambda k: dev)
+            _check_exchange_result(raw4, cuts4, got, infos, views)
+            raw3 = b"1,2,3\n" * 30000
+            cuts3 = [0, 7, 7, 100, 100000, len(raw3)]
+            got, infos, views = _exchange_chain(ctxs, exs, raw3, cuts3, lambda k: dev, window=4096)
+            _check_exchange_result(raw3, cuts3, got, infos, views)
+            assert [i["epoch"] for i in infos] == [4] * G
+            for e in exs:
+                e.close()
+            for c in ctxs:
+                c.close()
+        finally:
+            os.environ.pop("CSVB200_KERNEL", None)
+
+
+def test_exchange_missing_rank_times_out_not_hangs():
+    """A rank whose lower rank never posts gets CSVB200_ERR_EXCHANGE after the timeout: the wait is bounded."""
+    import torch
+    os.environ["CSVB200_EXCHANGE_TIMEOUT_MS"] = "50"
+    try:
+        ctxs = [cs.Context(0) for _ in range(2)]
+        exs = [c.exchange(k, 2) for k, c in enumerate(ctxs)]
+        cs.Exchange.connect_local(exs)
+        raw = b"a,b,c\n" * 50000
+        buf = torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()).to("cuda:0")
+        idx = ctxs[1].index_build_shard_exchange(exs[1], buf.data_ptr(), len(raw), 12345)   # rank 0 never builds
+        with pytest.raises(cs.GpuError) as ei:
+            idx.sync()
+        assert "exchange" in str(ei.value)
+        idx.free()
+        for e in exs:
+            e.close()
+        for c in ctxs:
+            c.close()
+    finally:
+        os.environ.pop("CSVB200_EXCHANGE_TIMEOUT_MS", None)
+
+
+def _multi_cases():
+    q, _ = gen.quoted(40 << 20, seed=44)
+    raw2 = (b'aa,bb"\n,cc,dd\n' * 300000) + b'x,y\n'
+    return [("quoted40M", q.tobytes()), ("misleading", raw2), ("tiny", b"a,b\n1,2\n" * 20)]
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_multi_one_gpu_listed_several_times(pinned):
+    """csvb200_multi_*: ONE byte slice in, ONE contiguous index out, the file cut at unaligned offsets across the
+    listed devices.  Listing device 0 four times runs the whole protocol (uploads, exchange, bases, the
+    misprediction re-index, placement of every segment in the caller's array) on a single GPU."""
+    import torch
+    m = cs.Multi([0, 0, 0, 0])
+    for name, raw in _multi_cases():
+        want = O.closed_form_numpy(raw)
+        a = np.frombuffer(raw, dtype=np.uint8)
+        if pinned:
+            h_in = torch.from_numpy(a.copy()).pin_memory()
+            h_out = torch.zeros(want.size + 8, dtype=torch.int64).pin_memory()
+            ln = m.index_build_to_host(h_in.data_ptr(), a.size, h_out.data_ptr(), h_out.numel())
+            got = h_out.numpy()[:ln].view(np.uint64)
+        else:
+            got = m.index_build(a)
+        assert got.size == want.size and (got == want).all(), name
+        st = m.stats()
+        assert st["entries"] == want.size
+        if name == "misleading":
+            assert st["redone_mask"] != 0
+    # explicit cuts: inside a quoted field, between the quotes of an escape, between CR and LF
+    body = b'id,"text, with ""escapes"" and\r\nnewlines",tail\r\n' * 4000
+    raw4 = b"h1,h2,h3\r\n" + body
+    cuts = [0, raw4.index(b"text"), raw4.index(b'""') + 1, raw4.index(b"\r\n", 50) + 1, len(raw4)]
+    got = m.index_build(np.frombuffer(raw4, dtype=np.uint8), cuts=cuts)
+    assert (got == O.closed_form_numpy(raw4)).all()
+    with pytest.raises(BufferError):
+        out = np.zeros(10, dtype=np.uint64)
+        m.index_build_to_host(np.frombuffer(raw4, dtype=np.uint8).ctypes.data, len(raw4), out.ctypes.data, out.size)
+    m.close()
+
+
+def test_multi_and_exchange_on_two_gpus():
+    """Real peer memory: two devices of one process, host threads running concurrently, rows crossing NVLink."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    G = min(torch.cuda.device_count(), 8)
+    m = cs.Multi(list(range(G)))
+    for name, raw in _multi_cases():
+        got = m.index_build(np.frombuffer(raw, dtype=np.uint8))
+        assert (got == O.closed_form_numpy(raw)).all(), name
+    m.close()
+
+
+def test_c_caller_of_the_multi_gpu_abi():
+    """a C program with no Python / torch in the process indexes one buffer across the GPUs of the box
+    through libcsvb200.so alone and equals the oracle (with one visible GPU the device is listed twice)."""
+    import json
+    import subprocess
+    import torch
+    from csv_simd_b200 import build as cbuild
+    so = cbuild.build()
+    oso = O.build()
+    ndev = max(2, min(torch.cuda.device_count(), 8))
+    devs = list(range(ndev)) if torch.cuda.device_count() >= 2 else [0] * ndev
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "test_multi")
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", os.path.join(root, "include"), "-I",
+                               os.path.join(root, "oracle"), os.path.join(root, "tests", "c", "test_multi.c"), "-o", exe,
+                               "-L", os.path.dirname(so), "-lcsvb200", "-L", os.path.dirname(oso), "-lcsv_oracle",
+                               "-Wl,-rpath," + os.path.dirname(so), "-Wl,-rpath," + os.path.dirname(oso)])
+        env = dict(os.environ, CSVB200_TEST_DEVICES=",".join(str(x) for x in devs))
+        out = subprocess.run([exe, str(ndev), str(48 << 20)], capture_output=True, text=True, env=env, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        rep = json.loads(out.stdout.strip().splitlines()[-1])
+        assert rep["equal_oracle"] is True and rep["ndev"] == ndev
