@@ -129,6 +129,8 @@ SIGNATURES = {
                                                     C.c_void_p, C.c_void_p, C.c_size_t]),
     "csvb200_validate_utf8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, C.POINTER(C.c_int)]),
     "csvb200_validate_utf8_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_index_validation": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), u64p]),
+    "csvb200_index_validate_utf8": (C.c_int, [C.c_void_p, u64p]),
     "csvb200_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "csvb200_index_load": (C.c_int, [C.c_void_p, C.c_char_p, vpp]),
     "csvb200_block_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),

@@ -14,6 +14,7 @@ from .errors import raise_for
 BUILD_DEFAULT = 0
 BUILD_KEEP_BYTES = 1
 BUILD_STRICT_MIN64 = 2
+BUILD_VALIDATE = 4
 FIELD_RAW = 0
 FIELD_UNQUOTE = 1
 FIELD_TRIM = 2
@@ -438,6 +439,18 @@ class StructureIndex:
     def shard_verify(self, d_gathered: int, world: int, d_final_out: int = 0):
         self.ctx._check(self._lib.csvb200_index_shard_verify(self._h, C.c_void_p(d_gathered), world,
                                                              C.c_void_p(d_final_out or 0)))
+
+    def validation(self):
+        """BUILD_VALIDATE by-products of the build launch -> (is_ascii, CR / LF bytes outside quotes)."""
+        a, nl = C.c_int(), C.c_uint64()
+        self.ctx._check(self._lib.csvb200_index_validation(self._h, C.byref(a), C.byref(nl)))
+        return bool(a.value), int(nl.value)
+
+    def validate_utf8(self):
+        """from_utf8's valid_up_to (None = well-formed), reading only the tiles the build flagged as non-ASCII."""
+        v = C.c_uint64()
+        self.ctx._check(self._lib.csvb200_index_validate_utf8(self._h, C.byref(v)))
+        return None if v.value == 0xFFFFFFFFFFFFFFFF else int(v.value)
 
     def shard_info(self) -> dict:
         """csvb200_index_shard_info (exchange builds): base slot, entries, true carry-in, whether it was re-indexed."""

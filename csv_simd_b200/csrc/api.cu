@@ -138,6 +138,24 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
         p.shard_par = idx->d_shard_par;
         p.shard_rank = idx->shard_rank;
         p.tune = ctx->tune;
+        // kernel choice: the TMA pipeline for anything of size, the one-tile-per-CTA kernel for small
+        // inputs; CSVB200_KERNEL=simple|tma forces one (tests cross-check the two against each other)
+        bool use_tma = tma_path_usable(n);
+        if (ctx->kernel_override == 1) use_tma = false;
+        if (ctx->kernel_override == 2 && n >= 128) use_tma = true;
+        if (idx->validate) {
+            // by-products: newline count and non-ASCII flag accumulate in the zeroed head of the scratch, the per-tile
+            // non-ASCII bitmap belongs to the index (K7 later visits the flagged tiles only)
+            const size_t words = (size_t)(num_tiles + 31) / 32;
+            if (!idx->d_nonascii) CU_TRY(ctx, cudaMallocAsync((void**)&idx->d_nonascii, words * sizeof(uint32_t), ctx->stream));
+            CU_TRY(ctx, cudaMemsetAsync(idx->d_nonascii, 0, words * sizeof(uint32_t), ctx->stream));
+            idx->flag_tile_bytes = build_flag_tile_bytes(n, use_tma, ctx->tune);
+            p.validate = 1u;
+            p.nonascii_bitmap = idx->d_nonascii;
+            p.nl_out = reinterpret_cast<unsigned long long*>(ctx->d_scratch + 16);
+            p.hi_out = reinterpret_cast<uint32_t*>(ctx->d_scratch + 24);
+            p.ex_done = reinterpret_cast<uint32_t*>(ctx->d_scratch + 4);
+        }
         if (idx->speculative) {
             uint64_t* d_carry = ctx->d_cells + idx->carry_cell * kCellWords;
             p.carry = d_carry;
@@ -163,11 +181,6 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             }
         }
         if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
-        // kernel choice: the TMA pipeline for anything of size, the one-tile-per-CTA kernel for small
-        // inputs; CSVB200_KERNEL=simple|tma forces one (tests cross-check the two against each other)
-        bool use_tma = tma_path_usable(n);
-        if (ctx->kernel_override == 1) use_tma = false;
-        if (ctx->kernel_override == 2 && n >= 128) use_tma = true;
         if (use_tma)
             CU_TRY(ctx, launch_index_build_tma(p, ctx->stream));
         else
@@ -178,7 +191,7 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             ctx->timed = true;
         }
         if (!ctx->host_result)
-            CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, kCellWords * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU_TRY(ctx, cudaEventRecord(idx->done, ctx->stream));
     idx->synced = false;
@@ -208,7 +221,7 @@ int new_index(csvb200_ctx* ctx, csvb200_index** out)
 int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity, uint64_t pos_bias,
                         int emit_sentinel, csvb200_index** out, const uint32_t* d_shard_par = nullptr,
                         uint32_t shard_rank = 0, uint64_t* d_result2 = nullptr, bool speculative = false,
-                        uint64_t predict_window = 0, csvb200_exchange* ex = nullptr)
+                        uint64_t predict_window = 0, csvb200_exchange* ex = nullptr, bool validate = false)
 {
     if (!ctx || !out || (n && !dev_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
     if ((reinterpret_cast<uintptr_t>(dev_bytes) & 15u) != 0)
@@ -225,6 +238,7 @@ int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint3
     idx->d_shard_par = d_shard_par;
     idx->shard_rank = shard_rank;
     idx->d_result2 = d_result2;
+    idx->validate = validate;
     if (ex) {
         idx->ex = ex;
         idx->ex_epoch = ++ex->epoch;
@@ -507,7 +521,44 @@ int csvb200_index_build_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n
 {
     if (ctx && (flags & CSVB200_BUILD_STRICT_MIN64) && n < 64)
         return fail(ctx, CSVB200_ERR_INPUT_TOO_SMALL, "n < 64: the reference panics on this input");
-    return build_device_common(ctx, dev_bytes, n, 0u, 0ull, 1, out);
+    return build_device_common(ctx, dev_bytes, n, 0u, 0ull, 1, out, nullptr, 0, nullptr, false, 0, nullptr,
+                               (flags & CSVB200_BUILD_VALIDATE) != 0);
+}
+
+int csvb200_index_validation(csvb200_index* idx, int* is_ascii, uint64_t* newlines_outside_quotes)
+{
+    if (!idx) return CSVB200_ERR_INVALID_ARG;
+    if (!idx->validate) return fail(idx->ctx, CSVB200_ERR_INVALID_STATE, "index was built without CSVB200_BUILD_VALIDATE");
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    if (is_ascii) *is_ascii = idx->any_nonascii ? 0 : 1;
+    if (newlines_outside_quotes) *newlines_outside_quotes = idx->newlines;
+    return CSVB200_OK;
+}
+
+int csvb200_index_validate_utf8(csvb200_index* idx, uint64_t* valid_up_to)
+{
+    if (!idx || !valid_up_to) return CSVB200_ERR_INVALID_ARG;
+    if (!idx->validate) return fail(idx->ctx, CSVB200_ERR_INVALID_STATE, "index was built without CSVB200_BUILD_VALIDATE");
+    int rc = csvb200_index_sync(idx);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    *valid_up_to = UINT64_MAX;
+    if (!idx->any_nonascii || idx->n == 0) return CSVB200_OK;   // ASCII is well-formed UTF-8: nothing to read again
+    const uint8_t* bytes = idx->d_bytes_owned ? idx->d_bytes_owned : idx->src;
+    if (!bytes) return fail(ctx, CSVB200_ERR_INVALID_STATE, "index was built without CSVB200_BUILD_KEEP_BYTES");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CellLease lease(ctx, 1);
+    if (!lease.ok()) return fail(ctx, CSVB200_ERR_OOM, "no free result cell (4095 live index objects)");
+    uint64_t* d_cell = ctx->d_cells + lease.first * kCellWords;
+    uint64_t* h_cell = ctx->h_cells + lease.first * kCellWords;
+    CU_TRY(ctx, cudaMemsetAsync(d_cell, 0xff, sizeof(uint64_t), ctx->stream));
+    CU_TRY(ctx, launch_utf8_validate_flagged(bytes, idx->n, idx->d_nonascii, idx->flag_tile_bytes, d_cell, ctx->stream));
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(h_cell, d_cell, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *valid_up_to = h_cell[0];
+    return CSVB200_OK;
 }
 
 int csvb200_index_build_shard_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t carry_parity,
@@ -613,7 +664,8 @@ int csvb200_index_build(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, u
     CU_TRY(ctx, d_bytes.alloc(((n + 15) & ~size_t(15)) + 16, ctx->stream));
     int rc = upload(ctx, d_bytes.as<uint8_t>(), host_bytes, n);
     csvb200_index* idx = nullptr;
-    if (!rc) rc = build_device_common(ctx, d_bytes.p, n, 0u, 0ull, 1, &idx);
+    if (!rc) rc = build_device_common(ctx, d_bytes.p, n, 0u, 0ull, 1, &idx, nullptr, 0, nullptr, false, 0, nullptr,
+                                      (flags & CSVB200_BUILD_VALIDATE) != 0);
     if (!rc) rc = csvb200_index_sync(idx);  // resolves a capacity overflow while the bytes are still here
     if (rc) {
         if (idx) csvb200_index_free(idx);
@@ -1087,6 +1139,10 @@ int csvb200_index_sync(csvb200_index* idx)
             return fail(ctx, CSVB200_ERR_EXCHANGE, "exchange: a lower rank never posted its row for this build (timeout), or lapped the mailbox ring");
         if (len <= idx->cap) {
             idx->len = len;
+            if (idx->validate) {
+                idx->any_nonascii = idx->n ? (int)(h_cell[2] & 1u) : 0;
+                idx->newlines = idx->n ? h_cell[3] : 0;
+            }
             idx->synced = true;
             return CSVB200_OK;
         }
@@ -1139,6 +1195,7 @@ void csvb200_index_free(csvb200_index* idx)
     cudaSetDevice(ctx->device);
     if (idx->d_index && !idx->borrowed) cudaFreeAsync(idx->d_index, ctx->stream);
     if (idx->d_bytes_owned) cudaFreeAsync(idx->d_bytes_owned, ctx->stream);
+    if (idx->d_nonascii) cudaFreeAsync(idx->d_nonascii, ctx->stream);
     if (idx->done) cudaEventDestroy(idx->done);
     cudaGetLastError();
     // (a cell released while its launch is still in flight is safe: the next holder's launch follows it in stream order)

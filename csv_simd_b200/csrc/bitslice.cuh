@@ -124,6 +124,31 @@ CSVB_HD void bitplanes32(const uint32_t w[8], uint32_t x[8])
     delta_swap_pair<1, 0x55555555u>(x[6], x[7]);
 }
 
+// classify32 plus the two by-products the planes give away for one more LOP3 each (CSVB200_BUILD_VALIDATE):
+//   nl : CR / LF (separators with bit 5 clear; ',' = 0x2C has it set)
+//   hi : bytes >= 0x80 (plane 7) -- is_ascii of the reference (src/reader.rs:26-132) is "no such byte"
+struct Masks32x {
+    uint32_t quote, sep, nl, hi;
+};
+
+CSVB_HD Masks32x classify32x(const uint32_t w[8])
+{
+    uint32_t x[8];
+    bitplanes32(w, x);
+    const uint32_t P0 = x[0], P1 = x[1], P2 = x[2], P3 = x[3];
+    const uint32_t P4 = x[4], P5 = x[5], P6 = x[6], P7 = x[7];
+    const uint32_t c = ~(P7 | P6 | P4);
+    const uint32_t u = (P5 ^ P0) & P2;
+    const uint32_t v = ~(P5 | P2 | P0);
+    const uint32_t m = (u & ~P1) | (v & P1);
+    Masks32x r;
+    r.sep = c & P3 & m;
+    r.quote = c & ~P3 & (P5 & ~P2 & ~P0) & P1;
+    r.nl = r.sep & ~P5;
+    r.hi = P7;
+    return r;
+}
+
 CSVB_HD Masks32 classify32(const uint32_t w[8])
 {
     uint32_t x[8];

@@ -98,6 +98,12 @@ struct csvb200_index {
     // speculative sharded build: carry cell {0, carry parity, decisive quote found, redo flag} (device / pinned mirror)
     bool speculative = false;
     bool verified = false;
+    // CSVB200_BUILD_VALIDATE: by-products of the build launch
+    bool validate = false;
+    uint32_t* d_nonascii = nullptr;         // one bit per look-back tile of flag_tile_bytes input bytes
+    uint64_t flag_tile_bytes = 0;
+    int any_nonascii = 0;
+    uint64_t newlines = 0;                  // CR / LF bytes outside quotes
     csvb200_exchange* ex = nullptr;         // built with the exchange inside the launch (csvb200_index_build_shard_exchange)
     uint64_t ex_epoch = 0;
     size_t carry_cell = SIZE_MAX;

@@ -43,6 +43,7 @@ struct __align__(1024) Smem {
         uint16_t stage[kTileBytes + 8];
     };
     uint32_t warp_agg[kWarps];
+    uint32_t warp_nl[kWarps];   // (validate) as in index_build_tma.cu
     WarpState warp_state[kWarps];
     uint32_t tile;
     uint32_t pin;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
     __syncthreads();
 
     // ---- 2. each thread: its 128 contiguous bytes (one swizzle row) -> quote / separator masks ----
-    uint32_t q[kGroups], s[kGroups];
+    uint32_t q[kGroups], s[kGroups], nlm[kGroups], hi = 0u;
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
         uint32_t w[8];
@@ -116,9 +117,11 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
             w[4 * i + 2] = v.z;
             w[4 * i + 3] = v.w;
         }
-        const Masks32 m = classify32(w);
+        const Masks32x m = classify32x(w);
         q[g] = m.quote;
         s[g] = m.sep;
+        nlm[g] = m.nl;
+        hi |= m.hi;
     }
 
     // ---- 3. quote regions inside the warp (relative to the warp start) ----
@@ -161,11 +164,23 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
     }
     const uint32_t exc = inc - packed;
     if (lane == 31) sm.warp_agg[warp] = inc | (warp_par << 31);
+    if (p.validate) {
+        uint32_t n0 = 0u, nt = 0u;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            n0 += __popc(nlm[g] & ~x[g]);
+            nt += __popc(nlm[g]);
+        }
+        const uint32_t nsum = __reduce_add_sync(0xffffffffu, n0 | (nt << 16));
+        const uint32_t anyhi = __any_sync(0xffffffffu, hi != 0u) ? 1u : 0u;
+        if (lane == 31) sm.warp_nl[warp] = nsum | (anyhi << 31);
+    }
     __syncthreads();  // also: every thread is done reading sm.in
 
     // ---- 4. warp 0: scan the 8 warp aggregates, publish, look back ----
     if (warp == 0) {
         uint32_t par = 0u, o0 = 0u, o1 = 0u;
+        uint32_t nl_a = 0u, nl_b = 0u, any_hi = 0u;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
             const uint32_t v = sm.warp_agg[w];
@@ -177,6 +192,13 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
             }
             o0 += par ? wa1 : wa0;
             o1 += par ? wa0 : wa1;
+            if (p.validate) {
+                const uint32_t nv = sm.warp_nl[w];
+                const uint32_t n0 = nv & 0xffffu, n1 = ((nv >> 16) & 0x7fffu) - n0;
+                nl_a += par ? n1 : n0;
+                nl_b += par ? n0 : n1;
+                any_hi |= nv >> 31;
+            }
             par ^= v >> 31;
         }
         // (par, o0, o1) is the tile aggregate
@@ -202,6 +224,14 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
             }
             if (tile == 0u && p.write_sentinel && p.cap > 0) p.index[0] = 0ull;
             if (p.total_out != nullptr && (o0 | o1) != 0u) atomicAdd(p.total_out, (unsigned long long)(o0 + o1));
+            if (p.validate) {
+                const uint32_t nl = pin ? nl_b : nl_a;
+                if (nl) atomicAdd(p.nl_out, (unsigned long long)nl);
+                if (any_hi) {
+                    atomicOr(p.hi_out, 1u);
+                    atomicOr(p.nonascii_bitmap + (tile >> 5), 1u << (tile & 31u));
+                }
+            }
             exchange_if_last(p);
         }
     }

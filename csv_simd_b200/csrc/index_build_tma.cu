@@ -70,14 +70,19 @@ struct TmaShape {
     static constexpr int kSuperBytes = kSub_ * kTile;
     static constexpr int kSlots = 2;                       // TMA ring depth in sub-tiles
 };
-using ShapeA = TmaShape<2, 2, 8192, 2>;   // 2 CTAs / SM, 99 KB each, 64 KiB per descriptor (round 1)
-using ShapeB = TmaShape<3, 1, 5120, 2>;   // 3 CTAs / SM, 75 KB each: one staging buffer
-using ShapeD = TmaShape<2, 2, 8192, 4>;   // 2 CTAs / SM, 128 KiB per descriptor
-using ShapeE = TmaShape<3, 1, 5120, 4>;   // 3 CTAs / SM, 128 KiB per descriptor
-using ShapeF = TmaShape<3, 1, 5120, 2, 2>;   // 3 CTAs / SM, two super-tiles of skew
-using ShapeG = TmaShape<2, 2, 8192, 2, 2>;   // 2 CTAs / SM, two super-tiles of skew
+using ShapeA = TmaShape<2, 2, 8192, 2>;          // 2 CTAs / SM, 99 KB each, 64 KiB per descriptor (round 1)
+using ShapeB = TmaShape<3, 1, 5120, 2>;          // 3 CTAs / SM, 75 KB each: one staging buffer (default since round 2)
 using ShapeH = TmaShape<2, 1, 7680, 2, 1, 12>;   // 2 CTAs / SM x 12 worker warps: 48 KiB sub-tiles, 96 KiB per descriptor
-using ShapeI = TmaShape<1, 2, 12288, 2, 1, 16>;  // 1 CTA / SM x 16 worker warps: 64 KiB sub-tiles, 128 KiB per descriptor
+// Measured on the 1 GiB configs, kernel ms cfg2 / cfg3 (gpurun_out kv2-kv6, round 2):
+//   A 0.395 / 0.346   B 0.391 / 0.342   H 0.401 / 0.344
+//   kSub = 4 (128 KiB per descriptor): 0.433 / 0.369 at 2 CTAs (36 pending mask registers), 0.539 / 0.453 at 3 (spills)
+//   kSkew = 2: 0.391 / 0.347 at 2 CTAs, 0.423 / 0.366 at 3 (spills);  1 CTA x 16 worker warps: 0.436 / 0.367
+//   look-back windows of 64 / 128 descriptors: 0.401 / 0.351 and 0.427 / 0.372;  re-polling one descriptor instead
+//   of the window: no change.
+// With every look-back answered on its first poll (the descriptors of a previous build of the same bytes left in place:
+// CSVB200_TUNE bit 0x400, a timing experiment) B runs 0.363 / 0.306 ms: the chain costs 7 % / 11 %, it is the
+// workers waiting for their prefix (ncu: 11.7 % of the samples on that wait against 1.2 %), and none of the above
+// moved it -- the wait follows the slowest of the ~440 tiles in flight, not the window, skew or descriptor size.
 // (Tried and dropped: a ring of three 16 KiB half-stages shared by two warp groups, to fit double-buffered staging
 //  into 70 KB.  It is NOT sound: the groups alternate on a slot, one group can run a whole phase ahead of the other,
 //  and a parity wait cannot express that; it read stale data on the 1 GiB inputs.)
@@ -101,11 +106,13 @@ struct __align__(1024) SmemTma {
     uint32_t tile_id[S::kSlots];            // super-tile id of the part in each slot
     uint32_t agg_tile[S::kRing];
     uint32_t warp_agg[S::kRing][S::kSub][S::kWorkers];
+    // CSVB200_BUILD_VALIDATE: per warp {newlines if entered outside quotes [15:0], newlines in all [30:16], any byte >= 0x80 [31]}
+    uint32_t warp_nl[S::kRing][S::kSub][S::kWorkers];
     PrefixInfo<S::kSub, S::kWorkers> pref[S::kRing];
 };
 
 // three CTAs per SM: 3 x (dynamic + 1 KiB reserved per CTA) must fit the SM's 228 KiB
-static_assert(sizeof(SmemTma<ShapeB>) <= 75 * 1024 && sizeof(SmemTma<ShapeF>) <= 75 * 1024, "3 CTAs / SM need <= 75 KiB each");
+static_assert(sizeof(SmemTma<ShapeB>) <= 75 * 1024, "3 CTAs / SM need <= 75 KiB each");
 static_assert(sizeof(SmemTma<ShapeH>) <= 113 * 1024, "2 CTAs / SM need <= 113 KiB each");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -268,7 +275,10 @@ __device__ __forceinline__ void compact_super(SmemTma<S>& sm, const BuildParams&
     for (int sub = 0; sub < S::kSub; ++sub) compact_sub<S>(sm, p, t.sub[sub], pi, sub, t.tile, it * S::kSub + sub, tid, warp);
 }
 
-template <class S>
+// kVal: CSVB200_BUILD_VALIDATE by-products; kEx: the cross-GPU exchange in the epilogue of the last CTA.  Both are
+// compile-time so that the plain build keeps the register allocation it was tuned with (with the exchange code merely
+// present the 64-register shape measured 0.401 instead of 0.391 ms on cfg2).
+template <class S, bool kVal, bool kEx>
 __global__ void __launch_bounds__(S::kThreadsAll, S::kMinBlocks)
 index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap tmap)
 {
@@ -328,6 +338,8 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
     } else if (warp == S::kLookbackWarp) {
         // ===== scan of warp aggregates + decoupled look-back =====
         uint64_t cta_total = 0ull;   // separators (inside + outside quotes) of this CTA's super-tiles (lane 0)
+        uint64_t cta_nl = 0ull;      // (validate) newlines outside quotes of this CTA's super-tiles
+        uint32_t cta_hi = 0u;        // (validate) a byte >= 0x80 was seen
         for (uint32_t it = 0;; ++it) {
             const uint32_t b = it % kRing;
             mbar_wait(&sm.agg_full[b], (it / kRing) & 1u);
@@ -337,6 +349,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             // fold the kSub x 8 warp aggregates in file order; remember the state entering every warp
             // and the (parity, c0, c1) composite at every sub-tile boundary
             uint32_t par = 0u, o0 = 0u, o1 = 0u;
+            uint32_t nl_a = 0u, nl_b = 0u, any_hi = 0u;   // newlines outside quotes if the super-tile is entered outside / inside
             uint32_t sub_par[kSub], sub_o0[kSub], sub_o1[kSub];
 #pragma unroll
             for (int sub = 0; sub < kSub; ++sub) {
@@ -355,6 +368,13 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                     }
                     o0 += par ? wa1 : wa0;
                     o1 += par ? wa0 : wa1;
+                    if (kVal) {
+                        const uint32_t nv = sm.warp_nl[b][sub][w];
+                        const uint32_t n0 = nv & 0xffffu, n1 = ((nv >> 16) & 0x7fffu) - n0;
+                        nl_a += par ? n1 : n0;
+                        nl_b += par ? n0 : n1;
+                        any_hi |= nv >> 31;
+                    }
                     par ^= v >> 31;
                 }
             }
@@ -383,13 +403,24 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 if (tile == p.num_tiles - 1) write_result(p, cend, pend);
                 if (tile == 0u && p.write_sentinel && p.cap > 0) p.index[0] = 0ull;
                 cta_total += (uint64_t)(o0 + o1);
+                if (kVal) {
+                    cta_nl += pin ? nl_b : nl_a;
+                    if (any_hi) {
+                        cta_hi = 1u;
+                        atomicOr(p.nonascii_bitmap + (tile >> 5), 1u << (tile & 31u));
+                    }
+                }
                 mbar_arrive(&sm.pref_full[b]);
             }
             __syncwarp();
         }
         if (lane == 0) {
             if (p.total_out != nullptr && cta_total != 0ull) atomicAdd(p.total_out, (unsigned long long)cta_total);
-            exchange_if_last(p);
+            if (kVal) {
+                if (cta_nl != 0ull) atomicAdd(p.nl_out, (unsigned long long)cta_nl);
+                if (cta_hi) atomicOr(p.hi_out, 1u);
+            }
+            if (kVal || kEx) exchange_if_last(p);
         }
     } else {
         // ===== workers =====
@@ -426,7 +457,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                     }
                 }
                 // ---- classify: 128 contiguous bytes (one swizzle row) per thread ----
-                uint32_t q[kGroups];
+                uint32_t q[kGroups], nlm[kGroups], hi = 0u;
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
                     uint32_t w[8];
@@ -439,9 +470,18 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                         w[4 * i + 2] = v.z;
                         w[4 * i + 3] = v.w;
                     }
-                    const Masks32 m = classify32(w);
-                    q[g] = m.quote;
-                    tr.s[g] = m.sep;
+                    if (kVal) {
+                        const Masks32x m = classify32x(w);
+                        q[g] = m.quote;
+                        tr.s[g] = m.sep;
+                        nlm[g] = m.nl;
+                        hi |= m.hi;
+                    } else {
+                        const Masks32 m = classify32(w);
+                        q[g] = m.quote;
+                        tr.s[g] = m.sep;
+                        nlm[g] = 0u;
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty[st]);  // slot can be refilled
@@ -479,6 +519,17 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 }
                 tr.exc = inc - packed;
                 if (lane == 31) sm.warp_agg[b][sub][warp] = inc | (warp_par << 31);
+                if (kVal) {
+                    uint32_t n0 = 0u, nt = 0u;
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        n0 += __popc(nlm[g] & ~tr.x[g]);
+                        nt += __popc(nlm[g]);
+                    }
+                    const uint32_t nsum = __reduce_add_sync(0xffffffffu, n0 | (nt << 16));
+                    const uint32_t anyhi = __any_sync(0xffffffffu, hi != 0u) ? 1u : 0u;
+                    if (lane == 31) sm.warp_nl[b][sub][warp] = nsum | (anyhi << 31);
+                }
             }
             if (lane == 31) {
                 if (warp == 0) sm.agg_tile[b] = cur.tile;
@@ -533,7 +584,7 @@ struct ShapeState {
     int grid_cap[kMaxDevices] = {};
 };
 
-template <class S>
+template <class S, bool kVal = false, bool kEx = false>
 cudaError_t launch_shape(const BuildParams& p_in, cudaStream_t stream)
 {
     static ShapeState state;
@@ -560,14 +611,14 @@ cudaError_t launch_shape(const BuildParams& p_in, cudaStream_t stream)
     {
         std::lock_guard<std::mutex> lock(state.mu);
         if (state.grid_cap[dev] == 0) {
-            e = cudaFuncSetAttribute(index_build_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(index_build_tma_kernel<S, kVal, kEx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(SmemTma<S>));
             if (e != cudaSuccess) return e;
-            cudaFuncSetAttribute(index_build_tma_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            cudaFuncSetAttribute(index_build_tma_kernel<S, kVal, kEx>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
             int sms = 148, per_sm = 0;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, index_build_tma_kernel<S>, S::kThreadsAll,
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, index_build_tma_kernel<S, kVal, kEx>, S::kThreadsAll,
                                                               sizeof(SmemTma<S>));
             if (e != cudaSuccess) return e;
             if (per_sm < 1) return cudaErrorLaunchOutOfResources;
@@ -576,25 +627,28 @@ cudaError_t launch_shape(const BuildParams& p_in, cudaStream_t stream)
         grid_cap = state.grid_cap[dev];
     }
     const unsigned grid = (unsigned)(p.num_tiles < (uint32_t)grid_cap ? p.num_tiles : (uint32_t)grid_cap);
-    index_build_tma_kernel<S><<<grid, S::kThreadsAll, sizeof(SmemTma<S>), stream>>>(p, tmap);
+    index_build_tma_kernel<S, kVal, kEx><<<grid, S::kThreadsAll, sizeof(SmemTma<S>), stream>>>(p, tmap);
     return cudaGetLastError();
 }
 
 }  // namespace
 
+uint64_t build_flag_tile_bytes(uint64_t n, bool use_tma, uint32_t tune)
+{
+    (void)n;
+    (void)tune;
+    return use_tma ? (uint64_t)ShapeB::kSuperBytes : (uint64_t)kTileBytes;   // validate builds always use the default shape
+}
+
 cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream)
 {
-    // CSVB200_TUNE bits 12-14 force a shape (A/B of the shapes on the same box); 0 = the default
+    if (p.validate) return p.ex.peers ? launch_shape<ShapeB, true, true>(p, stream) : launch_shape<ShapeB, true, false>(p, stream);
+    if (p.ex.peers) return launch_shape<ShapeB, false, true>(p, stream);
+    // CSVB200_TUNE bits 12-15 force a shape (A/B of the shapes on the same box); 0 = the default
     switch ((p.tune >> 12) & 15u) {
     case 1: return launch_shape<ShapeA>(p, stream);
-    case 2: return launch_shape<ShapeB>(p, stream);
-    case 3: return launch_shape<ShapeD>(p, stream);
-    case 4: return launch_shape<ShapeE>(p, stream);
-    case 5: return launch_shape<ShapeF>(p, stream);
-    case 6: return launch_shape<ShapeG>(p, stream);
     case 7: return launch_shape<ShapeH>(p, stream);
-    case 8: return launch_shape<ShapeI>(p, stream);
-    default: return launch_shape<ShapeB>(p, stream);   // r02: 0.391 / 0.342 ms on cfg2 / cfg3 against 0.395 / 0.346 for A
+    default: return launch_shape<ShapeB>(p, stream);
     }
 }
 

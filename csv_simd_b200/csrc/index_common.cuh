@@ -59,7 +59,7 @@ __device__ __forceinline__ uint64_t global_timer_ns()
 // all-gathered array): the true carry-in parity of this shard (XOR of the lower shards' parities, parity = end ^ used),
 // the entries the lower shards emit under THEIR true carries (flipping a carry swaps inside / outside separators, so
 // the other count is total - entries), and whether this shard's guess was wrong.
-static __device__ __noinline__ void exchange_post_and_resolve(const ExchangeArgs& ex, uint64_t entries, uint64_t end_parity,
+static __device__ __noinline__ void exchange_post_and_resolve(const ExchangeArgs ex, uint64_t entries, uint64_t end_parity,
                                                        uint64_t used, uint64_t total)
 {
     const uint64_t off = ((ex.epoch % kExRing) * kExMaxWorld) * kExRowWords;
@@ -153,10 +153,22 @@ __device__ __forceinline__ void write_result(const BuildParams& p, uint64_t cend
 // while other CTAs may still be compacting -- the NVLink round trip hides behind the tail of the launch.
 __device__ __forceinline__ void exchange_if_last(const BuildParams& p)
 {
-    if (p.ex.peers == nullptr) return;
+    if (p.ex_done == nullptr) return;
     __threadfence();
     if (atomicAdd(p.ex_done, 1u) != gridDim.x - 1u) return;
     __threadfence();
+    if (p.validate) {
+        // every CTA has added its newline count / non-ASCII flag: publish them next to {entries, end parity}
+        const uint64_t nl = ld_volatile_u64(reinterpret_cast<const uint64_t*>(p.nl_out));
+        const uint64_t hi = *reinterpret_cast<volatile const uint32_t*>(p.hi_out);
+        p.result[2] = hi;
+        p.result[3] = nl;
+        if (p.result_host != nullptr) {
+            p.result_host[2] = hi;
+            p.result_host[3] = nl;
+        }
+    }
+    if (p.ex.peers == nullptr) return;
     const uint64_t entries = ld_volatile_u64(p.result + 0), endp = ld_volatile_u64(p.result + 1);
     const uint64_t total = p.total_out != nullptr ? ld_volatile_u64(reinterpret_cast<const uint64_t*>(p.total_out)) : 0ull;
     const uint64_t used = (virtual_prefix_desc(p) >> 61) & 1ull;

@@ -85,7 +85,14 @@ struct BuildParams {
     // exchange inside the launch (multi-GPU, see ExchangeArgs): the last CTA to finish its look-back role posts this
     // shard's row to every peer's mailbox and resolves the carry chain of the lower ranks
     ExchangeArgs ex;
-    uint32_t* ex_done;       // CTAs whose look-back role is over; zeroed before launch (scratch)
+    uint32_t* ex_done;       // CTAs whose look-back role is over; zeroed before launch (scratch); needed by ex / validate
+    // by-products of the classification (CSVB200_BUILD_VALIDATE): newlines (CR or LF) outside quotes and "any byte
+    // >= 0x80", accumulated per CTA into the zeroed scratch words nl_out / hi_out and copied by the last CTA into
+    // result[3] / result[2]; nonascii_bitmap has one bit per look-back tile (flag_tile_bytes of input each)
+    uint32_t validate;
+    unsigned long long* nl_out;
+    uint32_t* hi_out;
+    uint32_t* nonascii_bitmap;
 };
 
 // one tile per CTA, plain loads: small inputs and cross-check of the TMA kernel
@@ -154,6 +161,12 @@ cudaError_t launch_gather_slots(const uint64_t* index, uint64_t index_len, const
 // K7 ASCII / UTF-8 validation (validate.cu): result[0] (preset UINT64_MAX) <- start of the first ill-formed
 // sequence, result[1] (preset 0) <- 1 when any byte is >= 0x80
 cudaError_t launch_utf8_validate(const uint8_t* in, uint64_t n, uint64_t* result, cudaStream_t stream);
+// the same over the tiles (tile_bytes each) whose bit is set in `bitmap` only: the build kernel flags the tiles that
+// hold a byte >= 0x80, every other tile is ASCII and leads (and owes) no multi-byte sequence
+cudaError_t launch_utf8_validate_flagged(const uint8_t* in, uint64_t n, const uint32_t* bitmap, uint64_t tile_bytes,
+                                         uint64_t* result, cudaStream_t stream);
+// bytes per bit of the non-ASCII bitmap for an input of n bytes (depends on the kernel the build picks)
+uint64_t build_flag_tile_bytes(uint64_t n, bool use_tma, uint32_t tune);
 
 // K6 column materialisation (materialize.cu)
 struct MaterializeParams {

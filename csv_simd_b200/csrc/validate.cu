@@ -97,7 +97,56 @@ __global__ void __launch_bounds__(256) utf8_validate_kernel(const uint8_t* __res
     }
 }
 
+// Only the tiles the build kernel flagged (a byte >= 0x80 somewhere inside): one CTA per flagged tile at a time.
+// A tile that is not flagged is pure ASCII, so it neither leads a multi-byte sequence nor owes continuation bytes to
+// a flagged neighbour's look-behind / look-ahead -- judging the flagged tiles alone gives from_utf8's answer.
+__global__ void __launch_bounds__(256) utf8_validate_flagged_kernel(const uint8_t* __restrict__ in, uint64_t n,
+                                                                    const uint32_t* __restrict__ bitmap, uint64_t tile_bytes,
+                                                                    uint64_t* __restrict__ result)
+{
+    const uint64_t ntiles = (n + tile_bytes - 1) / tile_bytes;
+    const uint64_t groups_per_tile = tile_bytes / 32;
+    uint64_t bad = UINT64_MAX;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (!((bitmap[t >> 5] >> (t & 31u)) & 1u)) continue;
+        for (uint64_t k = threadIdx.x; k < groups_per_tile; k += blockDim.x) {
+            const uint64_t i0 = t * tile_bytes + 32 * k;
+            if (i0 >= n) break;
+            uint32_t w[8];
+            load_group(in, n, i0, w);
+            uint32_t o = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o |= w[j];
+            if (o & 0x80808080u) {
+                const uint64_t r = judge_group(in, n, i0, w);
+                bad = r < bad ? r : bad;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, bad, d);
+        bad = o < bad ? o : bad;
+    }
+    if ((threadIdx.x & 31u) == 0u && bad != UINT64_MAX)
+        atomicMin(reinterpret_cast<unsigned long long*>(result), (unsigned long long)bad);
+}
+
 }  // namespace
+
+cudaError_t launch_utf8_validate_flagged(const uint8_t* in, uint64_t n, const uint32_t* bitmap, uint64_t tile_bytes,
+                                         uint64_t* result, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t blocks = (n + tile_bytes - 1) / tile_bytes;
+    const uint64_t max_blocks = (uint64_t)sms * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    utf8_validate_flagged_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, n, bitmap, tile_bytes, result);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_utf8_validate(const uint8_t* in, uint64_t n, uint64_t* result, cudaStream_t stream)
 {

@@ -59,6 +59,7 @@ typedef struct csvb200_range {
 #define CSVB200_BUILD_DEFAULT 0u
 #define CSVB200_BUILD_KEEP_BYTES 1u   /* keep the device copy of the input for csvb200_gather_fields */
 #define CSVB200_BUILD_STRICT_MIN64 2u /* mirror the reference's n < 64 panic as CSVB200_ERR_INPUT_TOO_SMALL */
+#define CSVB200_BUILD_VALIDATE 4u     /* by-products of the same launch: is_ascii, newlines outside quotes, non-ASCII tile map */
 
 int csvb200_version(void);
 const char* csvb200_status_string(int status);
@@ -350,6 +351,14 @@ int csvb200_materialize_column_device(csvb200_index* idx, uint32_t field_idx, ui
  * input is well-formed.  Device form: asynchronous, d_result = {valid_up_to, 1 if any byte >= 0x80}. */
 int csvb200_validate_utf8(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* valid_up_to, int* is_ascii);
 int csvb200_validate_utf8_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint64_t* d_result);
+
+/* Fused form (CSVB200_BUILD_VALIDATE on csvb200_index_build / _device): the classification already holds bit 7 of every
+ * byte and the CR / LF class, so the build launch itself reports is_ascii (src/reader.rs:26-132) and the number of
+ * CR / LF bytes outside quotes (= record terminators; rows for LF files, 2 x rows for CRLF files), and marks the
+ * 64 KiB tiles that hold a byte >= 0x80.  csvb200_index_validate_utf8 then reads ONLY the marked tiles (nothing at all
+ * for ASCII input) and returns what core::str::from_utf8 would: needs the input bytes (KEEP_BYTES / device build). */
+int csvb200_index_validation(csvb200_index* idx, int* is_ascii, uint64_t* newlines_outside_quotes);
+int csvb200_index_validate_utf8(csvb200_index* idx, uint64_t* valid_up_to);
 
 /* ---- on-disk index: 64-byte little-endian header {"CSVB2IDX", version 1, flags, input bytes, entries,
  * field_cnt, record_cnt, jump, end parity, wrapping sum of the entries} + the u64 entries ------------ */

@@ -86,3 +86,19 @@ def test_header_is_plain_c_and_links():
         assert out.returncode == 0, out.stderr
         v, *msg, cnt = out.stdout.split()
         assert int(v) == 100 and int(cnt) == len(names) and "Unsupported" in out.stdout
+
+
+def test_rust_sys_crate_is_in_sync_with_the_header():
+    """rust/csv-simd-b200-sys/src/lib.rs is generated from include/csvb200.h (there is no rustc in the image, so the
+    check is textual): the committed file is what the generator emits now, and it declares every exported symbol."""
+    import subprocess
+    import sys as _sys
+    subprocess.check_call([_sys.executable, os.path.join(ROOT, "tools", "gen_rust_sys.py"), "--check"])
+    text = open(os.path.join(ROOT, "rust", "csv-simd-b200-sys", "src", "lib.rs")).read()
+    for name in declared_symbols():
+        assert f"pub fn {name}(" in text, name
+    safe = "".join(open(os.path.join(ROOT, "rust", "csv-simd-b200", "src", f)).read()
+                   for f in ("lib.rs", "gpu.rs", "reader.rs", "record_source.rs"))
+    import re
+    for used in set(re.findall(r"sys::(csvb200_\w+)\(", safe)):
+        assert f"pub fn {used}(" in text, used

@@ -1013,14 +1013,12 @@ def test_gather_fields_on_a_shard_with_global_offset(ctx):
     for i in range(rec.size):
         a, b = int(rg[i, 0]), int(rg[i, 1])
         assert a >= cut and bytes(vals[int(offs[i]):int(offs[i + 1])]) == raw[a:b] and raw[a:b].isdigit()
-    # field 0 of the shard's first row starts at the sentinel's position 0 + 1 = global byte 1: not in this shard
+    # an index object that holds FEWER bytes than its positions refer to must refuse, never read out of bounds
+    wrapped = ctx.index_wrap_device(idx.device_ptr, len(idx), 100, d.data_ptr() + off)
+    wrapped.tape_init(16, False)
     with pytest.raises(cs.errors.ReferencePanic):   # CSVB200_ERR_OUT_OF_BOUNDS
-        wrapped = ctx.index_wrap_device(idx.device_ptr, len(idx), shard.size, d.data_ptr() + off)
-        try:
-            wrapped.tape_init(16, False)
-            wrapped.gather_fields(np.array([0], dtype=np.uint32), np.array([1], dtype=np.uint32))
-        finally:
-            wrapped.free()
+        wrapped.gather_fields(np.array([0], dtype=np.uint32), np.array([1], dtype=np.uint32))
+    wrapped.free()
     idx.free()
 
 
@@ -1232,3 +1230,56 @@ def test_c_caller_of_the_multi_gpu_abi():
         assert out.returncode == 0, out.stdout + out.stderr
         rep = json.loads(out.stdout.strip().splitlines()[-1])
         assert rep["equal_oracle"] is True and rep["ndev"] == ndev
+
+
+def test_build_validate_byproducts(forced_ctxs):
+    """CSVB200_BUILD_VALIDATE: is_ascii, the CR / LF count outside quotes and the per-tile non-ASCII map come out of
+    the build launch itself; validate_utf8 on the index then reads only flagged tiles.  Against the oracle's
+    is_ascii, the index itself (entries that are CR / LF) and CPython's decoder; both kernels; the index stays exact."""
+    import torch
+    rng = np.random.default_rng(11)
+    for kname in ("tma", "simple"):
+        c = forced_ctxs[kname]
+        dev = torch.device("cuda", c.device)
+        q, _ = gen.quoted(5 << 20, seed=45)
+        cases_ = [("ascii quoted", q.tobytes())]
+        u = bytearray(q.tobytes())
+        good = "é,ü – ✓,🙂".encode()
+        for pos in (0, 65500, 65536 - 2, 3 * 65536 - 1, 1 << 20, len(u) - len(good)):   # incl. sequences that straddle 64 KiB tiles
+            u[pos:pos + len(good)] = good
+        cases_.append(("valid utf8", bytes(u)))
+        for bad_pos in (5, 65535, 2 * 65536, 4 * 65536 + 17, len(u) - 1):
+            v = bytearray(u)
+            v[bad_pos] = 0xFF
+            cases_.append((f"invalid at {bad_pos}", bytes(v)))
+        v = bytearray(q.tobytes())
+        v[65534:65536] = b"\xe2\x82"          # truncated 3-byte sequence: its last byte would sit in the next tile
+        cases_.append(("truncated at a tile edge", bytes(v)))
+        for _ in range(3):
+            v = bytearray(q.tobytes())
+            for pos in rng.integers(0, len(v) - 8, size=40):
+                v[pos] = int(rng.integers(0x80, 0x100))
+            cases_.append(("random high bytes", bytes(v)))
+        cases_.append(("small", ("a,b\n1,\"x\ny\"\r\n" * 20).encode() + "ö".encode()))
+        for name, raw in cases_:
+            a = np.frombuffer(raw, dtype=np.uint8)
+            d = torch.empty(a.size + 64, dtype=torch.uint8, device=dev)
+            d[:a.size].copy_(torch.from_numpy(a.copy()))
+            idx = c.index_build_device(d.data_ptr(), a.size, cs.BUILD_VALIDATE)
+            host = idx.to_host()
+            want = O.closed_form_numpy(raw)
+            assert host.size == want.size and (host == want).all(), (kname, name)
+            is_ascii, newlines = idx.validation()
+            assert is_ascii == O.is_ascii(raw), (kname, name)
+            assert newlines == int(np.isin(a[host[1:].astype(np.int64)], np.array([0x0D, 0x0A], dtype=np.uint8)).sum()), (kname, name)
+            assert idx.validate_utf8() == O.utf8_valid_up_to(raw), (kname, name)
+            idx.free()
+        # host form + KEEP_BYTES
+        raw = cases_[1][1]
+        idx = c.index_build(raw, cs.BUILD_VALIDATE | cs.BUILD_KEEP_BYTES)
+        assert idx.validation()[0] is False and idx.validate_utf8() is None
+        idx.free()
+        idx = c.index_build(raw)
+        with pytest.raises(cs.InvalidState):
+            idx.validation()
+        idx.free()
