@@ -372,15 +372,24 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         launches0 = ctx.launch_count()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []
         e0.record(stream)
         for i in range(steps):
             idx = step_device(resolve=False)
             idx.free()
+            if i < 64:   # per-step marks (diagnostic: a stall of one step shows up as max >> median)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                marks.append(ev)
             if sharded and (i + 1) % 512 == 0 and i + 1 < steps:
                 barrier()   # the mailbox ring holds 1024 builds: no rank may run further ahead of the slowest one
         e1.record(stream)
         barrier()
-        ms_total = all_max(e0.elapsed_time(e1))
+        ms_mine = e0.elapsed_time(e1)
+        per = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        res["step_ms_median_max_rank"] = [float(statistics.median(per)), float(max(per))] if per else None
+        res["ms_per_step_by_rank"] = [float(v) / steps for v in gather_obj(ms_mine)]
+        ms_total = all_max(ms_mine)
         launches = ctx.launch_count() - launches0
         launches, E_total = all_sum_int(launches, E)
         res.update(ms_per_step=ms_total / steps, launches=launches, E_total=E_total)
@@ -538,7 +547,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     "what": "config 4 as written: ONE 8 GiB file (the same 8 row streams as the N=8 weak run) cut "
                             f"{world} ways at start + 37k + 13",
                     "total_bytes": ms_["total_bytes"], "bytes_per_gpu": ms_["n"], "index_entries": ms_["E_total"],
-                    "ms_per_step": ms_["ms_per_step"], "value": ms_["value"], "unit": UNIT,
+                    "ms_per_step": ms_["ms_per_step"], "ms_per_step_by_rank": ms_["ms_per_step_by_rank"],
+                    "step_ms_median_max_rank0": ms_["step_ms_median_max_rank"],
+                    "value": ms_["value"], "unit": UNIT,
                     "kernel_ms": ms_["kernel_ms"], "roofline_frac": ms_["achieved"] / peak,
                     "solo_ms_per_step": ms_["solo_ms_per_step"],
                     "efficiency_same_grammar": ms_["solo_ms_per_step"] / ms_["ms_per_step"],
@@ -563,7 +574,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config_block(wl, desc, n, m["total_bytes"], m["E_total"], world, numa_node,
-                                   host_numa_unbound_reason=numa_why),
+                                   host_numa_unbound_reason=numa_why, ms_per_step_by_rank=m["ms_per_step_by_rank"],
+                                   step_ms_median_max_rank0=m["step_ms_median_max_rank"]),
             "roofline": {"bound": "hbm", "kernel": "index_build_tma_kernel", "achieved": m["achieved"], "peak": peak,
                          "unit": "GB/s", "frac": m["achieved"] / peak, "traffic": traffic[0], "traffic_source": traffic[1],
                          "peak_source": peak_src,

@@ -105,6 +105,16 @@ SIGNATURES = {
     "csvb200_multi_index_build_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, szp, C.c_void_p, C.c_size_t,
                                                     szp]),
     "csvb200_multi_last_stats": (C.c_int, [C.c_void_p, C.POINTER(MultiStats)]),
+    "csvb200_multi_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, szp, vpp]),
+    "csvb200_multi_index_free": (None, [C.c_void_p]),
+    "csvb200_multi_index_len": (C.c_size_t, [C.c_void_p]),
+    "csvb200_multi_index_segment": (C.c_int, [C.c_void_p, C.c_int, u64p, u64p, C.POINTER(C.c_int)]),
+    "csvb200_multi_index_copy_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "csvb200_multi_tape_init": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, u32p, u64p]),
+    "csvb200_multi_seek_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_multi_seek_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_multi_seek_fields_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csvb200_multi_stream": (C.c_void_p, [C.c_void_p, C.c_int]),
     "csvb200_index_wrap_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, vpp]),
     "csvb200_index_sync": (C.c_int, [C.c_void_p]),
     "csvb200_index_len": (C.c_size_t, [C.c_void_p]),

@@ -369,6 +369,19 @@ class Multi:
             ln = self.index_build_to_host(a.ctypes.data, a.size, out.ctypes.data, out.size, cuts)
         return out[:ln]
 
+    def index_build_distributed(self, data, cuts=None) -> "MultiIndex":
+        """csvb200_multi_index_build: the index stays distributed over the devices, for lookups."""
+        a = _as_u8(data)
+        c = (C.c_size_t * len(cuts))(*cuts) if cuts is not None else None
+        h = C.c_void_p()
+        rc = self._lib.csvb200_multi_index_build(self._h, a.ctypes.data, a.size, c, C.byref(h))
+        if rc:
+            raise_for(rc, self._lib.csvb200_multi_last_error(self._h).decode("utf-8", "replace"))
+        return MultiIndex(self, h)
+
+    def stream(self, k: int) -> int:
+        return int(self._lib.csvb200_multi_stream(self._h, k) or 0)
+
     def stats(self) -> dict:
         st = _lib.MultiStats()
         self._lib.csvb200_multi_last_stats(self._h, C.byref(st))
@@ -382,6 +395,66 @@ class Multi:
     def __del__(self):
         try:
             self.close()
+        except Exception:
+            pass
+
+
+class MultiIndex:
+    """csvb200_multi_index: segment k of the index in device k's HBM; lookups read remote segments over NVLink."""
+
+    def __init__(self, multi: Multi, handle):
+        self.multi, self._h, self._lib = multi, handle, multi._lib
+
+    def _check(self, rc):
+        if rc:
+            raise_for(rc, self._lib.csvb200_multi_last_error(self.multi._h).decode("utf-8", "replace"))
+
+    def __len__(self):
+        return int(self._lib.csvb200_multi_index_len(self._h))
+
+    def segments(self):
+        out = []
+        for k in range(len(self.multi.devices)):
+            b, e, d = C.c_uint64(), C.c_uint64(), C.c_int()
+            self._check(self._lib.csvb200_multi_index_segment(self._h, k, C.byref(b), C.byref(e), C.byref(d)))
+            out.append({"base": b.value, "entries": e.value, "device": d.value})
+        return out
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(len(self), dtype=np.uint64)
+        self._check(self._lib.csvb200_multi_index_copy_out(self._h, out.ctypes.data, out.size))
+        return out
+
+    def tape_init(self, field_cnt: int, crlf: bool):
+        rc_, j = C.c_uint32(), C.c_uint64()
+        self._check(self._lib.csvb200_multi_tape_init(self._h, field_cnt, int(crlf), C.byref(rc_), C.byref(j)))
+        return rc_.value, j.value
+
+    def seek_fields(self, rec: np.ndarray, fld: np.ndarray) -> np.ndarray:
+        rec = np.ascontiguousarray(rec, dtype=np.uint32)
+        fld = np.ascontiguousarray(fld, dtype=np.uint32)
+        out = np.empty((rec.size, 2), dtype=np.uint64)
+        self._check(self._lib.csvb200_multi_seek_fields(self._h, rec.ctypes.data, fld.ctypes.data, rec.size, out.ctypes.data))
+        return out
+
+    def seek_records(self, rec: np.ndarray) -> np.ndarray:
+        rec = np.ascontiguousarray(rec, dtype=np.uint32)
+        out = np.empty((rec.size, 2), dtype=np.uint64)
+        self._check(self._lib.csvb200_multi_seek_records(self._h, rec.ctypes.data, rec.size, out.ctypes.data))
+        return out
+
+    def seek_fields_device(self, k: int, d_rec: int, d_fld: int, nq: int, d_out: int):
+        self._check(self._lib.csvb200_multi_seek_fields_device(self._h, k, C.c_void_p(d_rec), C.c_void_p(d_fld), nq,
+                                                               C.c_void_p(d_out)))
+
+    def free(self):
+        if getattr(self, "_h", None) and getattr(self.multi, "_h", None):
+            self._lib.csvb200_multi_index_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
         except Exception:
             pass
 

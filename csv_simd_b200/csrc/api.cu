@@ -181,6 +181,18 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             }
         }
         if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+        if (idx->speculative && !redo && !idx->verified) {
+            // predicted carry-in parity (rank 0 and empty shards: known to be 0) into the device cell the launch reads;
+            // the predictor sits right in front of the build so that the build can start under it (pdl_wait)
+            uint64_t* d_carry = ctx->d_cells + idx->carry_cell * kCellWords;
+            if (idx->shard_rank == 0 || n == 0) {
+                CU_TRY(ctx, cudaMemsetAsync(d_carry, 0, kCellWords * sizeof(uint64_t), ctx->stream));
+            } else {
+                CU_TRY(ctx, launch_predict_carry(idx->src, n, idx->predict_window, d_carry, ctx->stream));
+                ctx->launches += 1;
+                p.pdl_wait = (use_tma && !(ctx->tune & 0x800u)) ? 1u : 0u;   // CSVB200_TUNE bit 0x800: plain stream order (A/B)
+            }
+        }
         if (use_tma)
             CU_TRY(ctx, launch_index_build_tma(p, ctx->stream));
         else
@@ -251,19 +263,7 @@ int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint3
             return fail(ctx, CSVB200_ERR_OOM, "too many live index objects in this context (4095 result cells)");
         }
         idx->speculative = true;
-        uint64_t* d_carry = ctx->d_cells + idx->carry_cell * kCellWords;
-        cudaError_t e = cudaSuccess;
-        if (shard_rank == 0 || n == 0) {
-            e = cudaMemsetAsync(d_carry, 0, kCellWords * sizeof(uint64_t), ctx->stream);
-        } else {
-            e = launch_predict_carry(idx->src, n, predict_window ? predict_window : kDefaultPredictWindow, d_carry, ctx->stream);
-            ctx->launches += 1;
-        }
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            csvb200_index_free(idx);
-            return fail(ctx, CSVB200_ERR_CUDA, std::string("carry prediction: ") + cudaGetErrorString(e));
-        }
+        idx->predict_window = predict_window ? predict_window : kDefaultPredictWindow;
     }
     idx->cap = initial_cap(ctx, n);
     cudaError_t e = cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream);

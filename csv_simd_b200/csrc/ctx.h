@@ -107,6 +107,7 @@ struct csvb200_index {
     csvb200_exchange* ex = nullptr;         // built with the exchange inside the launch (csvb200_index_build_shard_exchange)
     uint64_t ex_epoch = 0;
     size_t carry_cell = SIZE_MAX;
+    uint64_t predict_window = 0;
     uint8_t* d_bytes_owned = nullptr;
     bool borrowed = false;                  // d_index belongs to the caller (csvb200_index_wrap_device): never freed here
     // Tape metadata (TapeCore::init)

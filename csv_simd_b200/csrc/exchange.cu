@@ -214,6 +214,17 @@ extern "C" int csvb200_exchange_counts(csvb200_exchange* ex, csvb200_index* idx,
 // ---------------------------------------------------------------------------------------------------------------
 // all GPUs of one process behind one call
 // ---------------------------------------------------------------------------------------------------------------
+struct csvb200_multi_index {
+    csvb200_multi* m = nullptr;
+    std::vector<csvb200_index*> seg;      // segment k on device k (global byte positions)
+    std::vector<uint8_t*> d_bytes;        // device copies of the shards (kept: csvb200_index_free does not own them)
+    std::vector<uint64_t> base;           // base[k] = global slot of seg[k][0]; base[G] = total length
+    SegmentTable table{};                 // the same, as the kernels take it
+    bool tape_ready = false;
+    uint32_t field_cnt = 0, record_cnt = 0;
+    uint64_t jump = 0;
+};
+
 struct csvb200_multi {
     std::vector<csvb200_ctx*> ctx;
     std::vector<csvb200_exchange*> ex;
@@ -299,6 +310,31 @@ int csvb200_multi_create(const int* devices, int ndev, csvb200_multi** out)
         m->ex.push_back(ex);
     }
     if (!rc && ndev > 1) rc = csvb200_exchange_connect_local(m->ex.data(), (uint32_t)ndev);
+    // index segments come from each device's stream-ordered pool: grant every other listed device access to it, so a
+    // lookup kernel on device j can read a segment that lives on device k (csvb200_multi_seek_fields)
+    for (int k = 0; k < ndev && !rc; ++k) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, devices[k]) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        std::vector<cudaMemAccessDesc> desc;
+        for (int j = 0; j < ndev; ++j) {
+            if (devices[j] == devices[k]) continue;
+            bool seen = false;
+            for (const cudaMemAccessDesc& d : desc) seen = seen || d.location.id == devices[j];
+            if (seen) continue;
+            cudaMemAccessDesc d{};
+            d.location.type = cudaMemLocationTypeDevice;
+            d.location.id = devices[j];
+            d.flags = cudaMemAccessFlagsProtReadWrite;
+            desc.push_back(d);
+        }
+        if (!desc.empty() && cudaMemPoolSetAccess(pool, desc.data(), desc.size()) != cudaSuccess) {
+            cudaGetLastError();
+            rc = CSVB200_ERR_EXCHANGE;
+        }
+    }
     if (rc) {
         csvb200_multi_destroy(m);
         return rc;
@@ -326,12 +362,14 @@ int csvb200_multi_last_stats(const csvb200_multi* m, csvb200_multi_stats* out)
     return CSVB200_OK;
 }
 
-int csvb200_multi_index_build_to_host(csvb200_multi* m, const uint8_t* host_bytes, size_t n, const size_t* cuts_in,
-                                      uint64_t* dst, size_t dst_cap, size_t* len_out)
+}  // extern "C"
+
+namespace {
+
+int make_cuts(csvb200_multi* m, size_t n, const size_t* cuts_in, std::vector<size_t>& cuts)
 {
-    if (!m || !len_out || (n && !host_bytes)) return mfail(m, CSVB200_ERR_INVALID_ARG, "null argument");
     const int G = (int)m->ctx.size();
-    std::vector<size_t> cuts(G + 1);
+    cuts.resize(G + 1);
     for (int k = 0; k <= G; ++k) {
         if (cuts_in) {
             cuts[k] = cuts_in[k];
@@ -342,17 +380,229 @@ int csvb200_multi_index_build_to_host(csvb200_multi* m, const uint8_t* host_byte
         if (k > 0 && cuts[k] < cuts[k - 1]) return mfail(m, CSVB200_ERR_INVALID_ARG, "cuts must be non-decreasing");
     }
     if (cuts[0] != 0 || cuts[G] != n) return mfail(m, CSVB200_ERR_INVALID_ARG, "cuts must span [0, n]");
+    return CSVB200_OK;
+}
+
+template <class F>
+void run_phase(csvb200_multi* m, F&& fn)
+{
+    const int G = (int)m->ctx.size();
+    if (m->shared_device || G == 1) {
+        for (int k = 0; k < G; ++k) fn(k);   // rank order: a rank only ever waits for lower ranks
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < G; ++k) th.emplace_back(fn, k);
+        for (std::thread& t : th) t.join();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int csvb200_multi_index_build(csvb200_multi* m, const uint8_t* host_bytes, size_t n, const size_t* cuts_in,
+                              csvb200_multi_index** out)
+{
+    if (!m || !out || (n && !host_bytes)) return mfail(m, CSVB200_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    const int G = (int)m->ctx.size();
+    std::vector<size_t> cuts;
+    int rc = make_cuts(m, n, cuts_in, cuts);
+    if (rc) return rc;
+    std::vector<ShardWork> work(G);
+    run_phase(m, [&](int k) { shard_phase1(m, k, host_bytes + cuts[k], cuts[k + 1] - cuts[k], cuts[k], &work[k]); });
+    for (int k = 0; k < G && !rc; ++k)
+        if (work[k].rc) rc = mfail(m, work[k].rc, "shard " + std::to_string(k) + ": " + work[k].err);
+    csvb200_multi_index* mi = rc ? nullptr : new (std::nothrow) csvb200_multi_index();
+    if (!rc && !mi) rc = mfail(m, CSVB200_ERR_OOM, "host allocation failed");
+    if (rc) {
+        for (int k = 0; k < G; ++k) {
+            cudaSetDevice(m->ctx[k]->device);
+            if (work[k].idx) csvb200_index_free(work[k].idx);
+            if (work[k].d_bytes) cudaFreeAsync(work[k].d_bytes, m->ctx[k]->stream);
+        }
+        cudaGetLastError();
+        return rc;
+    }
+    mi->m = m;
+    mi->table.nseg = (uint32_t)G;
+    for (int k = 0; k < G; ++k) {
+        mi->seg.push_back(work[k].idx);
+        mi->d_bytes.push_back(work[k].d_bytes);
+        mi->base.push_back(work[k].info.base);
+        mi->table.ptr[k] = csvb200_index_device_ptr(work[k].idx);
+        mi->table.base[k] = work[k].info.base;
+    }
+    mi->base.push_back(work[G - 1].info.base + work[G - 1].info.entries);
+    mi->table.base[G] = mi->base[G];
+    *out = mi;
+    return CSVB200_OK;
+}
+
+void csvb200_multi_index_free(csvb200_multi_index* mi)
+{
+    if (!mi) return;
+    for (size_t k = 0; k < mi->seg.size(); ++k) {
+        csvb200_ctx* ctx = mi->m->ctx[k];
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (mi->seg[k]) csvb200_index_free(mi->seg[k]);
+        if (mi->d_bytes[k]) cudaFreeAsync(mi->d_bytes[k], ctx->stream);
+    }
+    cudaGetLastError();
+    delete mi;
+}
+
+size_t csvb200_multi_index_len(const csvb200_multi_index* mi) { return mi ? (size_t)mi->base.back() : 0; }
+
+int csvb200_multi_index_segment(const csvb200_multi_index* mi, int k, uint64_t* base, uint64_t* entries, int* device)
+{
+    if (!mi || k < 0 || k >= (int)mi->seg.size()) return CSVB200_ERR_INVALID_ARG;
+    if (base) *base = mi->base[k];
+    if (entries) *entries = mi->base[k + 1] - mi->base[k];
+    if (device) *device = mi->m->ctx[k]->device;
+    return CSVB200_OK;
+}
+
+int csvb200_multi_index_copy_out(csvb200_multi_index* mi, uint64_t* dst, size_t dst_cap)
+{
+    if (!mi || !dst) return CSVB200_ERR_INVALID_ARG;
+    csvb200_multi* m = mi->m;
+    if (mi->base.back() > dst_cap) return mfail(m, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    const int G = (int)mi->seg.size();
+    std::vector<int> rcs(G, 0);
+    run_phase(m, [&](int k) {
+        rcs[k] = download(m->ctx[k], dst + mi->base[k], mi->table.ptr[k], (size_t)(mi->base[k + 1] - mi->base[k]));
+    });
+    for (int k = 0; k < G; ++k)
+        if (rcs[k]) return mfail(m, rcs[k], "segment " + std::to_string(k) + ": " + csvb200_last_error(m->ctx[k]));
+    return CSVB200_OK;
+}
+
+int csvb200_multi_tape_init(csvb200_multi_index* mi, uint32_t field_cnt, int crlf, uint32_t* record_cnt, uint64_t* jump)
+{
+    if (!mi) return CSVB200_ERR_INVALID_ARG;
+    const uint64_t len = mi->base.back();
+    const uint64_t j = crlf ? (uint64_t)field_cnt + 1 : (uint64_t)field_cnt;   // src/tape.rs:318-321
+    if (j == 0 || len == 0) return mfail(mi->m, CSVB200_ERR_INVALID_ARG, "field_cnt must be >= 1");
+    mi->field_cnt = field_cnt;
+    mi->jump = j;
+    mi->record_cnt = (uint32_t)((len - 1) / j);                                 // src/tape.rs:323-325
+    mi->tape_ready = true;
+    if (record_cnt) *record_cnt = mi->record_cnt;
+    if (jump) *jump = j;
+    if ((len - 1) % j != 0)                                                     // src/tape.rs:327,342-344
+        return mfail(mi->m, CSVB200_ERR_INVALID_CSV_FORMAT, csvb200_status_string(CSVB200_ERR_INVALID_CSV_FORMAT));
+    return CSVB200_OK;
+}
+
+// queries [q0, q1) on device k: host arrays in / out
+static int seek_share(csvb200_multi_index* mi, int k, const uint32_t* rec, const uint32_t* fld, size_t q0, size_t q1,
+                      csvb200_range* out, uint32_t* oob_out)
+{
+    csvb200_ctx* ctx = mi->m->ctx[k];
+    const size_t nq = q1 - q0;
+    if (nq == 0) return CSVB200_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf d_rec, d_fld, d_out, d_oob;
+    CU_TRY(ctx, d_rec.alloc(nq * sizeof(uint32_t), ctx->stream));
+    if (fld) CU_TRY(ctx, d_fld.alloc(nq * sizeof(uint32_t), ctx->stream));
+    CU_TRY(ctx, d_out.alloc(nq * sizeof(csvb200_range), ctx->stream));
+    CU_TRY(ctx, d_oob.alloc(sizeof(uint32_t), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_oob.p, 0, sizeof(uint32_t), ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_rec.p, rec + q0, nq * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (fld) CU_TRY(ctx, cudaMemcpyAsync(d_fld.p, fld + q0, nq * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    LookupParams p{};
+    p.index_len = mi->base.back();
+    p.record_cnt = mi->record_cnt;
+    p.field_cnt = mi->field_cnt;
+    p.row_size = (uint32_t)mi->jump;
+    p.rec = d_rec.as<uint32_t>();
+    p.fld = fld ? d_fld.as<uint32_t>() : nullptr;
+    p.nq = nq;
+    p.ranges = d_out.as<uint64_t>();
+    p.oob = d_oob.as<uint32_t>();
+    CU_TRY(ctx, launch_seek_sharded(p, mi->table, ctx->stream));
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(out + q0, d_out.p, nq * sizeof(csvb200_range), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(oob_out, d_oob.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CSVB200_OK;
+}
+
+static int multi_seek(csvb200_multi_index* mi, const uint32_t* rec, const uint32_t* fld, size_t nq, csvb200_range* out)
+{
+    if (!mi) return CSVB200_ERR_INVALID_ARG;
+    csvb200_multi* m = mi->m;
+    if (!mi->tape_ready) return mfail(m, CSVB200_ERR_INVALID_STATE, "csvb200_multi_tape_init has not been called");
+    if (nq == 0) return CSVB200_OK;
+    if (!rec || !out) return mfail(m, CSVB200_ERR_INVALID_ARG, "null argument");
+    // every device resolves an equal share of the batch; a slot owned by another GPU is one NVLink read
+    const int G = (int)mi->seg.size();
+    std::vector<int> rcs(G, 0);
+    std::vector<uint32_t> oob(G, 0);
+    run_phase(m, [&](int k) {
+        const size_t q0 = nq * k / G, q1 = nq * (k + 1) / G;
+        rcs[k] = seek_share(mi, k, rec, fld, q0, q1, out, &oob[k]);
+    });
+    for (int k = 0; k < G; ++k) {
+        if (rcs[k]) return mfail(m, rcs[k], "device " + std::to_string(k) + ": " + csvb200_last_error(m->ctx[k]));
+        if (oob[k]) return mfail(m, CSVB200_ERR_OUT_OF_BOUNDS, "lookup slot past the end of the index");
+    }
+    return CSVB200_OK;
+}
+
+int csvb200_multi_seek_fields(csvb200_multi_index* mi, const uint32_t* rec, const uint32_t* fld, size_t nq, csvb200_range* out)
+{
+    if (mi && nq && !fld) return mfail(mi->m, CSVB200_ERR_INVALID_ARG, "null argument");
+    return multi_seek(mi, rec, fld, nq, out);
+}
+
+int csvb200_multi_seek_records(csvb200_multi_index* mi, const uint32_t* rec, size_t nq, csvb200_range* out)
+{
+    return multi_seek(mi, rec, nullptr, nq, out);
+}
+
+// device arrays that live on device k in / out; asynchronous on that device's context stream (benchmarks)
+int csvb200_multi_seek_fields_device(csvb200_multi_index* mi, int k, const uint32_t* d_rec, const uint32_t* d_fld, size_t nq,
+                                     csvb200_range* d_out)
+{
+    if (!mi || k < 0 || k >= (int)mi->seg.size()) return CSVB200_ERR_INVALID_ARG;
+    csvb200_ctx* ctx = mi->m->ctx[k];
+    if (!mi->tape_ready) return mfail(mi->m, CSVB200_ERR_INVALID_STATE, "csvb200_multi_tape_init has not been called");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    LookupParams p{};
+    p.index_len = mi->base.back();
+    p.record_cnt = mi->record_cnt;
+    p.field_cnt = mi->field_cnt;
+    p.row_size = (uint32_t)mi->jump;
+    p.rec = d_rec;
+    p.fld = d_fld;
+    p.nq = nq;
+    p.ranges = reinterpret_cast<uint64_t*>(d_out);
+    p.oob = reinterpret_cast<uint32_t*>(ctx->d_cells + (kCells - 1) * kCellWords);
+    CU_TRY(ctx, launch_seek_sharded(p, mi->table, ctx->stream));
+    ctx->launches += 1;
+    return CSVB200_OK;
+}
+
+void* csvb200_multi_stream(csvb200_multi* m, int k)
+{
+    return (m && k >= 0 && k < (int)m->ctx.size()) ? (void*)m->ctx[k]->stream : nullptr;
+}
+
+int csvb200_multi_index_build_to_host(csvb200_multi* m, const uint8_t* host_bytes, size_t n, const size_t* cuts_in,
+                                      uint64_t* dst, size_t dst_cap, size_t* len_out)
+{
+    if (!m || !len_out || (n && !host_bytes)) return mfail(m, CSVB200_ERR_INVALID_ARG, "null argument");
+    const int G = (int)m->ctx.size();
+    std::vector<size_t> cuts;
+    {
+        int rc0 = make_cuts(m, n, cuts_in, cuts);
+        if (rc0) return rc0;
+    }
     const double t0 = now_s();
     std::vector<ShardWork> work(G);
-    auto run_phase = [&](auto&& fn) {
-        if (m->shared_device || G == 1) {
-            for (int k = 0; k < G; ++k) fn(k);   // rank order: a rank only ever waits for lower ranks
-        } else {
-            std::vector<std::thread> th;
-            for (int k = 0; k < G; ++k) th.emplace_back(fn, k);
-            for (std::thread& t : th) t.join();
-        }
-    };
     auto first_error = [&]() -> int {
         for (int k = 0; k < G; ++k)
             if (work[k].rc) return mfail(m, work[k].rc, "shard " + std::to_string(k) + ": " + work[k].err);
@@ -366,7 +616,7 @@ int csvb200_multi_index_build_to_host(csvb200_multi* m, const uint8_t* host_byte
         }
         cudaGetLastError();
     };
-    run_phase([&](int k) { shard_phase1(m, k, host_bytes + cuts[k], cuts[k + 1] - cuts[k], cuts[k], &work[k]); });
+    run_phase(m, [&](int k) { shard_phase1(m, k, host_bytes + cuts[k], cuts[k + 1] - cuts[k], cuts[k], &work[k]); });
     int rc = first_error();
     size_t total = 0;
     if (!rc) {
@@ -375,7 +625,7 @@ int csvb200_multi_index_build_to_host(csvb200_multi* m, const uint8_t* host_byte
         if (total > dst_cap || (total && !dst)) rc = mfail(m, CSVB200_ERR_CAPACITY, "destination index buffer too small");
     }
     if (!rc) {
-        run_phase([&](int k) { shard_phase2(m, k, dst, &work[k]); });
+        run_phase(m, [&](int k) { shard_phase2(m, k, dst, &work[k]); });
         rc = first_error();
     }
     m->stats = csvb200_multi_stats{};

@@ -337,6 +337,9 @@ __global__ void __launch_bounds__(kPredictThreads) predict_carry_kernel(const ui
 {
     __shared__ uint32_t s_warp[kPredictThreads / 32];
     __shared__ uint32_t s_res[3];   // found, predicted parity, running parity
+    // the index build behind this launch may start now (programmatic dependent launch): only the threads that read
+    // the cell wait for this grid to finish (BuildParams::pdl_wait)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t lim = n < window ? n : window;
     uint32_t run_par = 0u, pred = 0u, found = 0u;

@@ -627,8 +627,17 @@ cudaError_t launch_shape(const BuildParams& p_in, cudaStream_t stream)
         grid_cap = state.grid_cap[dev];
     }
     const unsigned grid = (unsigned)(p.num_tiles < (uint32_t)grid_cap ? p.num_tiles : (uint32_t)grid_cap);
-    index_build_tma_kernel<S, kVal, kEx><<<grid, S::kThreadsAll, sizeof(SmemTma<S>), stream>>>(p, tmap);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(S::kThreadsAll);
+    cfg.dynamicSmemBytes = sizeof(SmemTma<S>);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.pdl_wait ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, index_build_tma_kernel<S, kVal, kEx>, p, tmap);
 }
 
 }  // namespace

@@ -120,6 +120,7 @@ __device__ __forceinline__ uint64_t virtual_prefix_desc(const BuildParams& p)
 {
     uint64_t carry_count = p.carry_count;
     uint32_t carry_parity = p.carry_parity;
+    if (p.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // the predictor's cell is complete and visible
     if (p.carry != nullptr) {
         if (!p.carry_parity_only) carry_count = p.carry[0];
         carry_parity = (uint32_t)p.carry[1] & 1u;

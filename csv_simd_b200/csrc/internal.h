@@ -89,6 +89,10 @@ struct BuildParams {
     // by-products of the classification (CSVB200_BUILD_VALIDATE): newlines (CR or LF) outside quotes and "any byte
     // >= 0x80", accumulated per CTA into the zeroed scratch words nl_out / hi_out and copied by the last CTA into
     // result[3] / result[2]; nonascii_bitmap has one bit per look-back tile (flag_tile_bytes of input each)
+    // the launch was made with programmatic stream serialization right behind predict_carry_kernel: the threads that
+    // read the carry cell (the look-back of the first tiles, the epilogue) execute griddepcontrol.wait first, every
+    // other thread starts classifying while the predictor still runs
+    uint32_t pdl_wait;
     uint32_t validate;
     unsigned long long* nl_out;
     uint32_t* hi_out;
@@ -135,6 +139,15 @@ struct LookupParams {
     uint32_t* oob;           // incremented for queries whose index slot is out of bounds (reference would panic)
 };
 cudaError_t launch_seek(const LookupParams& p, cudaStream_t stream);
+// the same over an index that is distributed over several GPUs of one process: segment k holds the global slots
+// [base[k], base[k + 1]) and lives in device k's HBM, mapped into the launching device (peer access over NVLink).
+// p.index is ignored; p.index_len is the total length.
+struct SegmentTable {
+    const uint64_t* ptr[kExMaxWorld];
+    uint64_t base[kExMaxWorld + 1];
+    uint32_t nseg;
+};
+cudaError_t launch_seek_sharded(const LookupParams& p, const SegmentTable& seg, cudaStream_t stream);
 
 // gather the bytes of resolved ranges into a packed buffer: out[out_off[i] .. out_off[i+1]) = the input bytes
 // [start, end); ranges are GLOBAL positions, bytes[0] is global byte pos_bias and n bytes are addressable

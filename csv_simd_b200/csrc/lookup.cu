@@ -56,6 +56,47 @@ __global__ void __launch_bounds__(256) seek_kernel(const LookupParams p)
     }
 }
 
+// One entry of an index whose segments live on different GPUs: a register-resident search over <= 16 bases, then a
+// plain 8-byte load through the peer mapping (an NVLink read when the slot's owner is another GPU).
+__device__ __forceinline__ uint64_t sharded_entry(const SegmentTable& seg, uint64_t s)
+{
+    uint32_t k = 0;
+#pragma unroll
+    for (uint32_t j = 1; j < kExMaxWorld; ++j)
+        if (j < seg.nseg && s >= seg.base[j]) k = j;
+    return ldg_u64(seg.ptr[k] + (s - seg.base[k]));
+}
+
+__global__ void __launch_bounds__(256) seek_sharded_kernel(const LookupParams p, const SegmentTable seg)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < p.nq; q += stride) {
+        const uint32_t r = p.rec[q];
+        uint64_t start = UINT64_MAX, end = UINT64_MAX;
+        bool live = (uint32_t)(r + 1u) < p.record_cnt;
+        uint32_t s;
+        uint64_t e_slot;
+        if (p.fld != nullptr) {
+            const uint32_t f = p.fld[q];
+            live = live && f < p.field_cnt;
+            s = (uint32_t)(r + 1u) * p.row_size + f;     // u32 arithmetic, as the reference (src/record_source.rs:129)
+            e_slot = (uint64_t)s + 1;
+        } else {
+            s = (uint32_t)(r + 1u) * p.row_size;         // src/record_source.rs:83
+            e_slot = (uint64_t)s + p.field_cnt;
+        }
+        if (live) {
+            if (e_slot < p.index_len) {
+                start = sharded_entry(seg, s) + 1;
+                end = sharded_entry(seg, e_slot);
+            } else {
+                atomicAdd(p.oob, 1u);
+            }
+        }
+        asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.ranges + 2 * q), "l"(start), "l"(end) : "memory");
+    }
+}
+
 __global__ void __launch_bounds__(256) range_lengths_kernel(const uint64_t* __restrict__ ranges, uint64_t nq,
                                                             uint64_t* __restrict__ lens)
 {
@@ -99,6 +140,19 @@ cudaError_t launch_seek(const LookupParams& p, cudaStream_t stream)
     const uint64_t max_blocks = (uint64_t)sms * 32;
     if (blocks > max_blocks) blocks = max_blocks;
     seek_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_seek_sharded(const LookupParams& p, const SegmentTable& seg, cudaStream_t stream)
+{
+    if (p.nq == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t blocks = (p.nq + 255) / 256;
+    const uint64_t max_blocks = (uint64_t)sms * 32;
+    if (blocks > max_blocks) blocks = max_blocks;
+    seek_sharded_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, seg);
     return cudaGetLastError();
 }
 

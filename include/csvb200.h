@@ -251,6 +251,27 @@ int csvb200_multi_device_count(const csvb200_multi* m);
  * and bases over peer memory, and writes ONE contiguous index into dst: exactly reader::read's output. */
 int csvb200_multi_index_build_to_host(csvb200_multi* m, const uint8_t* host_bytes, size_t n, const size_t* cuts,
                                       uint64_t* dst, size_t dst_cap, size_t* len_out);
+/* The same build, leaving the index DISTRIBUTED over the devices (segment k in device k's HBM, global byte positions)
+ * for lookups: SURVEY 8e "the index stays distributed; lookups route the slot to the owning rank".  Here the routing
+ * is done by the memory system: every device has every segment mapped (peer access), a batch of (record, field)
+ * queries is split evenly over the devices and each lookup kernel reads index[s], index[s + 1] from whichever GPU owns
+ * them -- 16 bytes over NVLink per remote query, nothing is gathered or replicated.  RecordSource semantics as
+ * csvb200_seek_fields (src/record_source.rs:104-140). */
+typedef struct csvb200_multi_index csvb200_multi_index;
+int csvb200_multi_index_build(csvb200_multi* m, const uint8_t* host_bytes, size_t n, const size_t* cuts,
+                              csvb200_multi_index** out);
+void csvb200_multi_index_free(csvb200_multi_index* mi);
+size_t csvb200_multi_index_len(const csvb200_multi_index* mi);
+int csvb200_multi_index_segment(const csvb200_multi_index* mi, int k, uint64_t* base, uint64_t* entries, int* device);
+int csvb200_multi_index_copy_out(csvb200_multi_index* mi, uint64_t* dst, size_t dst_cap);
+int csvb200_multi_tape_init(csvb200_multi_index* mi, uint32_t field_cnt, int crlf, uint32_t* record_cnt, uint64_t* jump);
+int csvb200_multi_seek_fields(csvb200_multi_index* mi, const uint32_t* rec, const uint32_t* fld, size_t nq, csvb200_range* out);
+int csvb200_multi_seek_records(csvb200_multi_index* mi, const uint32_t* rec, size_t nq, csvb200_range* out);
+/* device arrays on device number k of the list; asynchronous on that device's stream (csvb200_multi_stream) */
+int csvb200_multi_seek_fields_device(csvb200_multi_index* mi, int k, const uint32_t* d_rec, const uint32_t* d_fld, size_t nq,
+                                     csvb200_range* d_out);
+void* csvb200_multi_stream(csvb200_multi* m, int k);
+
 typedef struct csvb200_multi_stats {
     double seconds, upload_seconds, download_seconds;
     uint64_t entries;

@@ -1283,3 +1283,58 @@ def test_build_validate_byproducts(forced_ctxs):
         with pytest.raises(cs.InvalidState):
             idx.validation()
         idx.free()
+
+
+def _check_multi_lookups(m, nfields=64, size=6 << 20):
+    data, rows = gen.unquoted(size, seed=45, nfields=nfields, modulus=10 ** 9)
+    raw = data.tobytes()
+    want_idx = O.closed_form_numpy(raw)
+    mi = m.index_build_distributed(data)
+    assert len(mi) == want_idx.size and (mi.to_host() == want_idx).all()
+    segs = mi.segments()
+    assert segs[0]["base"] == 0 and sum(s_["entries"] for s_ in segs) == want_idx.size
+    assert all(segs[k]["base"] + segs[k]["entries"] == segs[k + 1]["base"] for k in range(len(segs) - 1))
+    rc, jump = mi.tape_init(nfields, False)
+    assert (jump, rc) == O.tape_init(want_idx.size, nfields, False) and rc == rows + 1
+    nq = 200_000
+    rec, fld = gen.queries(nq, rc, nfields, seed=46)
+    rec[-2000:-1000] = rc - 1 + np.arange(1000, dtype=np.uint32)     # out of range -> None
+    fld[-1000:] = nfields + np.arange(1000, dtype=np.uint32) % 5
+    got = mi.seek_fields(rec, fld)
+    live = (rec + 1 < rc) & (fld < nfields)
+    s = (rec[live].astype(np.int64) + 1) * nfields + fld[live]
+    assert (got[live, 0] == want_idx[s] + 1).all() and (got[live, 1] == want_idx[s + 1]).all()
+    assert (got[~live] == U64MAX).all()
+    for i in range(0, nq, 4001):
+        w = O.seek_field(want_idx, len(raw), rc, nfields, False, int(rec[i]), int(fld[i]))
+        assert (w is None and got[i, 0] == U64MAX) or (int(got[i, 0]), int(got[i, 1])) == w
+    gr = mi.seek_records(rec[:5000])
+    for i in range(0, 5000, 53):
+        w = O.seek_record(want_idx, len(raw), rc, jump, nfields, int(rec[i]))
+        assert (int(gr[i, 0]), int(gr[i, 1])) == w
+    # a ragged file is reported exactly as TapeCore::init reports it (src/tape.rs:327,342-344)
+    mi2 = m.index_build_distributed(np.frombuffer(raw + b"1,2\n", dtype=np.uint8))
+    with pytest.raises(cs.InvalidCsvFormat):
+        mi2.tape_init(nfields, False)
+    with pytest.raises(cs.InvalidState):
+        m.index_build_distributed(data).seek_fields(rec[:10], fld[:10])
+    mi2.free()
+    mi.free()
+
+
+def test_multi_distributed_index_lookups_one_gpu():
+    """csvb200_multi_index_*: the index stays distributed (segment k on device k), a batch of lookups is split over the
+    devices and every kernel reads the slots it needs from whichever segment owns them.  Device 0 listed three times:
+    the segment table, the slot routing and the batch split are exercised on one GPU."""
+    m = cs.Multi([0, 0, 0])
+    _check_multi_lookups(m)
+    m.close()
+
+
+def test_multi_distributed_index_lookups_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    m = cs.Multi(list(range(min(torch.cuda.device_count(), 8))))
+    _check_multi_lookups(m, nfields=256, size=64 << 20)
+    m.close()
