@@ -137,6 +137,10 @@ SIGNATURES = {
                                              C.c_void_p, C.c_size_t, szp]),
     "csvb200_materialize_column_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                     C.c_void_p, C.c_void_p, C.c_size_t]),
+    "csvb200_materialize_columns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              vpp, vpp, szp, szp]),
+    "csvb200_materialize_columns_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                     vpp, vpp, szp]),
     "csvb200_validate_utf8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, C.POINTER(C.c_int)]),
     "csvb200_validate_utf8_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "csvb200_index_validation": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), u64p]),

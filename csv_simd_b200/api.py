@@ -613,6 +613,34 @@ class StructureIndex:
                                                                  C.byref(ln)))
         return offs, out
 
+    def materialize_columns(self, fields, first_record: int, nrec: int, flags: int = FIELD_RAW):
+        """csvb200_materialize_columns: several columns in one sweep -> [(offsets, values)] per requested field."""
+        f = np.ascontiguousarray(fields, dtype=np.uint32)
+        k = int(f.size)
+        offs = [np.zeros(nrec + 1, dtype=np.uint64) for _ in range(k)]
+        p_off = (C.c_void_p * k)(*[o.ctypes.data for o in offs])
+        lens = (C.c_size_t * k)()
+        caps = (C.c_size_t * k)()
+        rc = self._lib.csvb200_materialize_columns(self._h, f.ctypes.data, k, first_record, nrec, flags, p_off, None, caps, lens)
+        if rc not in (0, 9):      # CSVB200_ERR_CAPACITY sizes the outputs
+            self.ctx._check(rc)
+        vals = [np.empty(int(lens[c]), dtype=np.uint8) for c in range(k)]
+        if any(v.size for v in vals):
+            p_out = (C.c_void_p * k)(*[v.ctypes.data if v.size else None for v in vals])
+            caps = (C.c_size_t * k)(*[v.size for v in vals])
+            self.ctx._check(self._lib.csvb200_materialize_columns(self._h, f.ctypes.data, k, first_record, nrec, flags, p_off,
+                                                                  p_out, caps, lens))
+        return list(zip(offs, vals))
+
+    def materialize_columns_device(self, fields, first_record: int, nrec: int, flags: int, d_offsets, d_outs=None, out_caps=None):
+        f = np.ascontiguousarray(fields, dtype=np.uint32)
+        k = int(f.size)
+        p_off = (C.c_void_p * k)(*d_offsets)
+        p_out = (C.c_void_p * k)(*d_outs) if d_outs is not None else None
+        caps = (C.c_size_t * k)(*out_caps) if out_caps is not None else None
+        self.ctx._check(self._lib.csvb200_materialize_columns_device(self._h, f.ctypes.data, k, first_record, nrec, flags, p_off,
+                                                                     p_out, caps))
+
     def materialize_column_device(self, field_idx: int, first_record: int, nrec: int, flags: int, d_offsets: int,
                                   d_out: int, out_cap: int):
         self.ctx._check(self._lib.csvb200_materialize_column_device(self._h, field_idx, first_record, nrec, flags,

@@ -88,8 +88,38 @@ namespace {
 
 size_t initial_cap(const csvb200_ctx* ctx, size_t n)
 {
-    return (size_t)((unsigned __int128)n * ctx->reserve_num / ctx->reserve_den) + 4096;
+    const size_t by_ratio = (size_t)((unsigned __int128)n * ctx->reserve_num / ctx->reserve_den) + 4096;
+    if (ctx->reserve_explicit || ctx->density_hint <= 0.0 || n < (size_t(1) << 20)) return by_ratio;
+    const size_t by_hint = (size_t)((double)n * ctx->density_hint) + 4096;
+    return std::min(by_ratio, std::max(by_hint, n / 64 + 4096));
 }
+
+// a finished build of n bytes produced len entries: remember the density for the next reservation
+void observe_density(csvb200_ctx* ctx, size_t n, size_t len)
+{
+    if (n < (size_t(1) << 20)) return;
+    const double seen = 1.25 * (double)len / (double)n;
+    ctx->density_hint = std::max(seen, 0.9 * ctx->density_hint);
+}
+
+// worst-case reservation (one entry per byte) for the duration of a scope: re-index paths that must not overflow
+struct ReserveAll {
+    csvb200_ctx* ctx;
+    uint32_t num, den;
+    bool explicit_;
+    explicit ReserveAll(csvb200_ctx* c) : ctx(c), num(c->reserve_num), den(c->reserve_den), explicit_(c->reserve_explicit)
+    {
+        ctx->reserve_num = 1;
+        ctx->reserve_den = 1;
+        ctx->reserve_explicit = true;
+    }
+    ~ReserveAll()
+    {
+        ctx->reserve_num = num;
+        ctx->reserve_den = den;
+        ctx->reserve_explicit = explicit_;
+    }
+};
 
 // enqueue one build of idx->src[0..n) into idx->d_index (capacity idx->cap)
 // redo = the conditional second launch of a speculative shard build (runs only if the carry prediction was wrong)
@@ -486,6 +516,7 @@ int csvb200_ctx_set_reserve(csvb200_ctx* ctx, uint32_t num, uint32_t den)
     if (!ctx || den == 0) return fail(ctx, CSVB200_ERR_INVALID_ARG, "bad reserve ratio");
     ctx->reserve_num = num;
     ctx->reserve_den = den;
+    ctx->reserve_explicit = true;
     return CSVB200_OK;
 }
 
@@ -862,7 +893,10 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
                 }
                 copied = upto;
             }
-            if (c + 1 == nchunks) *len_out = upto;
+            if (c + 1 == nchunks) {
+                *len_out = upto;
+                observe_density(ctx, n, upto);
+            }
         }
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -951,14 +985,10 @@ int csvb200_shard_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
     int rc = pipeline_to_host(ctx, host_bytes, n, dst, dst_cap, len_out, o, &overflow, &job->dst_small);
     if (!rc && overflow) {
         // denser than the reserve: raise the reserve to the worst case for this context and go again
-        const uint32_t num = ctx->reserve_num, den = ctx->reserve_den;
-        ctx->reserve_num = 1;
-        ctx->reserve_den = 1;
+        ReserveAll worst(ctx);
         cudaFreeAsync(job->d_bytes, ctx->stream);
         job->d_bytes = nullptr;
         rc = pipeline_to_host(ctx, host_bytes, n, dst, dst_cap, len_out, o, &overflow, &job->dst_small);
-        ctx->reserve_num = num;
-        ctx->reserve_den = den;
     }
     if (rc) {
         if (job->d_bytes) cudaFreeAsync(job->d_bytes, ctx->stream);
@@ -997,13 +1027,8 @@ int csvb200_shard_job_verify(csvb200_shard_job* job, const uint64_t* d_gathered,
     o.d_bytes_in = job->d_bytes;
     o.d_result4 = job->d_result4;
     bool overflow = false;
-    const uint32_t num = ctx->reserve_num, den = ctx->reserve_den;
-    ctx->reserve_num = 1;    // a flipped carry can turn every masked separator into an entry
-    ctx->reserve_den = 1;
-    int rc = pipeline_to_host(ctx, job->host_bytes, job->n, job->dst, job->dst_cap, len_out, o, &overflow);
-    ctx->reserve_num = num;
-    ctx->reserve_den = den;
-    return rc;
+    ReserveAll worst(ctx);   // a flipped carry can turn every masked separator into an entry
+    return pipeline_to_host(ctx, job->host_bytes, job->n, job->dst, job->dst_cap, len_out, o, &overflow);
 }
 
 void csvb200_shard_job_free(csvb200_shard_job* job)
@@ -1060,12 +1085,8 @@ int csvb200_shard_build_to_host_exchange(csvb200_ctx* ctx, csvb200_exchange* ex,
         o.d_carry0 = d_carry;
         o.d_bytes_in = job->d_bytes;
         bool overflow = false;
-        const uint32_t num = ctx->reserve_num, den = ctx->reserve_den;
-        ctx->reserve_num = 1;    // a flipped carry can turn every masked separator into an entry
-        ctx->reserve_den = 1;
+        ReserveAll worst(ctx);   // a flipped carry can turn every masked separator into an entry
         rc = pipeline_to_host(ctx, host_bytes, n, dst, dst_cap, len_out, o, &overflow);
-        ctx->reserve_num = num;
-        ctx->reserve_den = den;
     } else if (job->dst_small) {
         rc = fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
     }
@@ -1139,6 +1160,7 @@ int csvb200_index_sync(csvb200_index* idx)
             return fail(ctx, CSVB200_ERR_EXCHANGE, "exchange: a lower rank never posted its row for this build (timeout), or lapped the mailbox ring");
         if (len <= idx->cap) {
             idx->len = len;
+            observe_density(ctx, idx->n, len);
             if (idx->validate) {
                 idx->any_nonascii = idx->n ? (int)(h_cell[2] & 1u) : 0;
                 idx->newlines = idx->n ? h_cell[3] : 0;
@@ -1642,6 +1664,110 @@ int csvb200_materialize_column(csvb200_index* idx, uint32_t field_idx, uint32_t 
     rc = materialize_enqueue(idx, field_idx, first_record, nrec, flags, d_off.as<uint64_t>(), d_out.as<uint8_t>(), total, false, true);
     if (rc) return rc;
     CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CSVB200_OK;
+}
+
+// several columns, one sweep per pass (materialize.cu: a thread owns a row and walks its requested fields)
+static int materialize_multi_enqueue(csvb200_index* idx, const uint32_t* fields, uint32_t ncols, uint32_t first_record,
+                                     uint32_t nrec, uint32_t flags, uint64_t* const* d_offsets, uint8_t* const* d_outs,
+                                     const size_t* out_caps, bool offsets_pass, bool write_pass)
+{
+    csvb200_ctx* ctx = idx->ctx;
+    MaterializeMultiParams p{};
+    p.index = idx->d_index;
+    p.index_len = idx->len;
+    p.bytes = idx->d_bytes_owned ? idx->d_bytes_owned : idx->src;
+    p.n = idx->n;
+    p.pos_bias = idx->pos_bias;
+    p.record_cnt = idx->record_cnt;
+    p.field_cnt = idx->field_cnt;
+    p.row_size = (uint32_t)idx->jump;
+    p.first_record = first_record;
+    p.nrec = nrec;
+    p.flags = flags;
+    p.ncols = ncols;
+    p.tiles = (nrec + 255) / 256;
+    for (uint32_t c = 0; c < ncols; ++c) {
+        p.field_idx[c] = fields[c];
+        p.offsets[c] = d_offsets[c];
+        p.out[c] = d_outs ? d_outs[c] : nullptr;
+        p.out_cap[c] = out_caps ? out_caps[c] : 0;
+    }
+    if (offsets_pass) {
+        const size_t sbytes = materialize_multi_scratch_bytes(nrec, ncols);
+        int rc = ensure_scratch(ctx, sbytes);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, ctx->stream));
+        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
+        p.tile_desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
+        if (nrec == 0)
+            for (uint32_t c = 0; c < ncols; ++c) CU_TRY(ctx, cudaMemsetAsync(d_offsets[c], 0, sizeof(uint64_t), ctx->stream));
+        CU_TRY(ctx, launch_materialize_multi_offsets(p, ctx->stream));
+        if (nrec) ctx->launches += 1;
+    }
+    if (write_pass && nrec) {
+        CU_TRY(ctx, launch_materialize_multi_write(p, ctx->stream));
+        ctx->launches += 1;
+    }
+    return CSVB200_OK;
+}
+
+int csvb200_materialize_columns_device(csvb200_index* idx, const uint32_t* fields, uint32_t ncols, uint32_t first_record,
+                                       uint32_t nrec, uint32_t flags, uint64_t* const* d_offsets, uint8_t* const* d_outs,
+                                       const size_t* out_caps)
+{
+    int rc = materialize_prepare(idx, flags);
+    if (rc) return rc;
+    if (!fields || !d_offsets || ncols == 0 || ncols > kMatMaxCols)
+        return fail(idx->ctx, CSVB200_ERR_INVALID_ARG, "1 <= ncols <= 32 and non-null arrays");
+    return materialize_multi_enqueue(idx, fields, ncols, first_record, nrec, flags, d_offsets, d_outs, out_caps, true,
+                                     d_outs != nullptr);
+}
+
+int csvb200_materialize_columns(csvb200_index* idx, const uint32_t* fields, uint32_t ncols, uint32_t first_record,
+                                uint32_t nrec, uint32_t flags, uint64_t* const* out_offsets, uint8_t* const* outs,
+                                const size_t* out_caps, size_t* out_lens)
+{
+    int rc = materialize_prepare(idx, flags);
+    if (rc) return rc;
+    csvb200_ctx* ctx = idx->ctx;
+    if (!fields || !out_offsets || !out_lens || ncols == 0 || ncols > kMatMaxCols)
+        return fail(ctx, CSVB200_ERR_INVALID_ARG, "1 <= ncols <= 32 and non-null arrays");
+    std::vector<DevBuf> d_off(ncols), d_out(ncols);
+    std::vector<uint64_t*> p_off(ncols);
+    std::vector<uint8_t*> p_out(ncols, nullptr);
+    std::vector<size_t> caps(ncols, 0);
+    for (uint32_t c = 0; c < ncols; ++c) {
+        if (!out_offsets[c]) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+        CU_TRY(ctx, d_off[c].alloc(((size_t)nrec + 1) * sizeof(uint64_t), ctx->stream));
+        p_off[c] = d_off[c].as<uint64_t>();
+    }
+    rc = materialize_multi_enqueue(idx, fields, ncols, first_record, nrec, flags, p_off.data(), nullptr, nullptr, true, false);
+    if (rc) return rc;
+    for (uint32_t c = 0; c < ncols; ++c)
+        CU_TRY(ctx, cudaMemcpyAsync(out_offsets[c], p_off[c], ((size_t)nrec + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    bool small = false, any = false;
+    for (uint32_t c = 0; c < ncols; ++c) {
+        const uint64_t total = out_offsets[c][nrec];
+        out_lens[c] = (size_t)total;
+        if (total > (out_caps ? out_caps[c] : 0)) small = true;
+        if (total) any = true;
+    }
+    if (small) return fail(ctx, CSVB200_ERR_CAPACITY, "materialize destination too small");
+    if (!any) return CSVB200_OK;
+    if (!outs) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    for (uint32_t c = 0; c < ncols; ++c) {
+        if (out_lens[c] && !outs[c]) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+        CU_TRY(ctx, d_out[c].alloc(out_lens[c], ctx->stream));
+        p_out[c] = d_out[c].as<uint8_t>();
+        caps[c] = out_lens[c];
+    }
+    rc = materialize_multi_enqueue(idx, fields, ncols, first_record, nrec, flags, p_off.data(), p_out.data(), caps.data(), false, true);
+    if (rc) return rc;
+    for (uint32_t c = 0; c < ncols; ++c)
+        if (out_lens[c]) CU_TRY(ctx, cudaMemcpyAsync(outs[c], p_out[c], out_lens[c], cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CSVB200_OK;
 }

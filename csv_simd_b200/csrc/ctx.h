@@ -51,6 +51,11 @@ struct csvb200_ctx {
     uint8_t* h_stage[csvb200::kStageBufs] = {nullptr, nullptr};
     cudaEvent_t stage_free[csvb200::kStageBufs] = {nullptr, nullptr};
     uint32_t reserve_num = 1, reserve_den = 3;
+    // entries per input byte seen by the builds of this context (x 1.25): once known, large builds reserve by it
+    // instead of by the 1/3 worst-case guess (a 4 GiB shard reserved 11.5 GB for a 1.9 GB index, and mapping a block of
+    // that size for the first time stalls a launch by ~0.3 s); an index that outgrows its reserve is rebuilt exactly
+    double density_hint = 0.0;
+    bool reserve_explicit = false;    // csvb200_ctx_set_reserve was called: the ratio is the caller's, no hint
     uint64_t launches = 0;
     int kernel_override = 0;  // 0 = auto, 1 = simple, 2 = tma (CSVB200_KERNEL)
     uint32_t tune = 0;        // CSVB200_TUNE experiment knob

@@ -198,6 +198,32 @@ struct MaterializeParams {
     uint32_t* ticket;        // zeroed
 };
 size_t materialize_scratch_bytes(uint32_t nrec);   // [128 B ticket cell][descriptors]
+
+// Several columns of the same records in ONE sweep: a thread owns a row and walks the requested fields of that row
+// (adjacent index slots, adjacent bytes: the sectors one column drags in serve its neighbours), so the input and the
+// index cross DRAM once per pass instead of once per column and pass.
+constexpr uint32_t kMatMaxCols = 32;
+struct MaterializeMultiParams {
+    const uint64_t* index;
+    uint64_t index_len;
+    const uint8_t* bytes;
+    uint64_t n;
+    uint64_t pos_bias;
+    uint32_t record_cnt, field_cnt, row_size;
+    uint32_t first_record, nrec;
+    uint32_t flags;
+    uint32_t ncols;
+    uint32_t field_idx[kMatMaxCols];
+    uint64_t* offsets[kMatMaxCols];   // per column [nrec + 1]
+    uint8_t* out[kMatMaxCols];        // per column packed values (write pass)
+    uint64_t out_cap[kMatMaxCols];
+    uint64_t* tile_desc;              // [ncols][tiles] look-back descriptors (zeroed)
+    uint32_t* ticket;                 // zeroed
+    uint32_t tiles;
+};
+size_t materialize_multi_scratch_bytes(uint32_t nrec, uint32_t ncols);
+cudaError_t launch_materialize_multi_offsets(const MaterializeMultiParams& p, cudaStream_t stream);
+cudaError_t launch_materialize_multi_write(const MaterializeMultiParams& p, cudaStream_t stream);
 cudaError_t launch_materialize_offsets(const MaterializeParams& p, cudaStream_t stream);
 cudaError_t launch_materialize_write(const MaterializeParams& p, cudaStream_t stream);
 

@@ -365,6 +365,18 @@ int csvb200_materialize_column(csvb200_index* idx, uint32_t field_idx, uint32_t 
 int csvb200_materialize_column_device(csvb200_index* idx, uint32_t field_idx, uint32_t first_record, uint32_t nrec,
                                       uint32_t flags, uint64_t* d_offsets, uint8_t* d_out, size_t out_cap);
 
+/* Several columns of the same records in ONE sweep per pass (ncols <= 32): a device thread owns a row and walks its
+ * requested fields, whose index slots and bytes sit next to each other, so the input and the index cross DRAM once
+ * per pass instead of once per column and pass (a single column of a row-major file touches one 32-byte sector of
+ * every row: ~14 x more traffic than the bytes it returns).  Arrays of ncols pointers / capacities; semantics per
+ * column exactly as csvb200_materialize_column. */
+int csvb200_materialize_columns(csvb200_index* idx, const uint32_t* fields, uint32_t ncols, uint32_t first_record,
+                                uint32_t nrec, uint32_t flags, uint64_t* const* out_offsets, uint8_t* const* outs,
+                                const size_t* out_caps, size_t* out_lens);
+int csvb200_materialize_columns_device(csvb200_index* idx, const uint32_t* fields, uint32_t ncols, uint32_t first_record,
+                                       uint32_t nrec, uint32_t flags, uint64_t* const* d_offsets, uint8_t* const* d_outs,
+                                       const size_t* out_caps);
+
 /* ---- input validation (the reference's is_ascii, src/reader.rs:26-132, and its dead UTF-8 checker,
  * src/avx/utf8check.rs; seek_record builds &str unchecked, src/record_source.rs:97-101) ----------- */
 /* One pass over the bytes: *is_ascii = no byte >= 0x80 (is_ascii's answer); *valid_up_to = what

@@ -1338,3 +1338,31 @@ def test_multi_distributed_index_lookups_two_gpus():
     m = cs.Multi(list(range(min(torch.cuda.device_count(), 8))))
     _check_multi_lookups(m, nfields=256, size=64 << 20)
     m.close()
+
+
+@pytest.mark.parametrize("flags", [0, 3])
+def test_materialize_columns_one_sweep_vs_oracle(ctx, flags):
+    """csvb200_materialize_columns: several columns of the same records in one sweep per pass; every column equals what
+    the single-column call and the oracle's scalar definition give (incl. an out-of-range field, empty ranges, a range
+    that runs past the last record, 17 columns = more columns than warps)."""
+    raw = _column_cases()
+    idx = ctx.index_build(raw, cs.BUILD_KEEP_BYTES)
+    rc, jump = idx.tape_init(3, False)
+    host = idx.to_host()
+    for fields, first, nrec in (([0, 1, 2], 0, rc - 1), ([2, 0], 17, 1000), ([1], 3, 700), ([1, 7, 2, 2], rc - 5, 20),
+                                ([0, 1], 5, 0), ([2, 1, 0] * 5 + [1, 2], 1024, 1100)):
+        got = idx.materialize_columns(fields, first, nrec, flags)
+        for f, (offs, out) in zip(fields, got):
+            w_offs, w_out = O.materialize_column(raw, host, rc, 3, False, f, first, nrec, flags)
+            assert (offs == w_offs).all(), (fields, f, first, nrec)
+            assert out.tobytes() == w_out, (fields, f, first, nrec)
+    idx.free()
+    # a wide quoted file: all 16 columns at once against the single-column kernel
+    q, _ = gen.quoted(3 << 20, seed=43)
+    idx = ctx.index_build(q, cs.BUILD_KEEP_BYTES)
+    rc, _ = idx.tape_init(16, True)
+    got = idx.materialize_columns(list(range(16)), 0, rc - 1, flags)
+    for f in (0, 1, 7, 15):
+        offs, out = idx.materialize_column(f, 0, rc - 1, flags)
+        assert (got[f][0] == offs).all() and got[f][1].tobytes() == out.tobytes()
+    idx.free()

@@ -110,6 +110,56 @@ def main():
             "cpu_baseline": {"value": k / cpu_s / 1e6, "unit": "Mvalues/s", "cores": 1, "kind": "port",
                              "sample": f"first {k} records, scalar definition in oracle/csv_oracle.c"},
             "parity": f"offsets and bytes of the first {k} records equal the oracle's"}), flush=True)
+        # ---- K6 multi: 1, 4, 8 and all 16 columns in one sweep per pass (csvb200_materialize_columns_device) ----
+        one_col_ms = ms
+        for cols in ([fld], [1, 5, 9, 13], list(range(1, 16, 2)), list(range(16))):
+            k_ = len(cols)
+            d_offs = [torch.empty(nrec + 1, dtype=torch.int64, device=dev) for _ in cols]
+            idx.materialize_columns_device(cols, 0, nrec, flags, [t_.data_ptr() for t_ in d_offs])
+            torch.cuda.synchronize()
+            totals = [int(t_[-1].item()) for t_ in d_offs]
+            d_outs = [torch.empty(max(tt, 1), dtype=torch.uint8, device=dev) for tt in totals]
+            ms_m = timed(stream, lambda: idx.materialize_columns_device(cols, 0, nrec, flags, [t_.data_ptr() for t_ in d_offs],
+                                                                         [t_.data_ptr() for t_ in d_outs], totals), a.steps)
+            # parity: every column equals the single-column kernel's output (which is pinned to the oracle above)
+            ok = True
+            for c_, f_ in enumerate(cols[:3]):
+                o1 = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
+                idx.materialize_column_device(f_, 0, nrec, flags, o1.data_ptr(), 0, 0)
+                v1 = torch.empty(max(totals[c_], 1), dtype=torch.uint8, device=dev)
+                idx.materialize_column_device(f_, 0, nrec, flags, o1.data_ptr(), v1.data_ptr(), totals[c_])
+                torch.cuda.synchronize()
+                ok = ok and bool(torch.equal(o1, d_offs[c_])) and bool(torch.equal(v1[:totals[c_]], d_outs[c_][:totals[c_]]))
+            assert ok
+            print(json.dumps({
+                "kernel": "materialize_multi_offsets_kernel + materialize_multi_write_kernel", "workload": wl, "columns": k_,
+                "metric": "values_materialised_per_sec", "value": k_ * nrec / (ms_m * 1e-3) / 1e6, "unit": "Mvalues/s",
+                "ms": ms_m, "ms_single_column_kernel": one_col_ms, "x_single_column": ms_m / one_col_ms,
+                "ms_if_looped_over_single_column": k_ * one_col_ms, "value_bytes": sum(totals),
+                "parity": "offsets and bytes of the first 3 columns equal the single-column kernels' output"}), flush=True)
+            del d_offs, d_outs
+        # ---- fused by-products: CSVB200_BUILD_VALIDATE against the plain build, same bytes ----
+        def build_plain():
+            ctx.index_build_device(d.data_ptr(), n).free()
+
+        def build_val():
+            ctx.index_build_device(d.data_ptr(), n, cs.BUILD_VALIDATE).free()
+        ms_plain = timed(stream, build_plain, a.steps)
+        ms_val = timed(stream, build_val, a.steps)
+        iv = ctx.index_build_device(d.data_ptr(), n, cs.BUILD_VALIDATE)
+        asc, newlines = iv.validation()
+        t0_ = time.perf_counter()
+        v_up = iv.validate_utf8()
+        flagged_s = time.perf_counter() - t0_
+        want_nl = int(np.isin(data[host[1:].astype(np.int64)], np.array([0x0D, 0x0A], dtype=np.uint8)).sum())
+        assert asc == O.is_ascii(data) and newlines == want_nl and v_up is None
+        iv.free()
+        print(json.dumps({
+            "kernel": "index_build_tma_kernel<validate>", "workload": wl, "metric": "csv_bytes_indexed_per_sec",
+            "ms_build_plain": ms_plain, "ms_build_with_byproducts": ms_val, "overhead": ms_val / ms_plain - 1.0,
+            "is_ascii": asc, "newlines_outside_quotes": newlines, "utf8_pass_over_flagged_tiles_ms": flagged_s * 1e3,
+            "parity": "is_ascii == reader::is_ascii restatement; newline count == CR/LF entries of the oracle-checked index"}),
+            flush=True)
         # ---- K7: ASCII / UTF-8 validation of the same bytes ----
         d_res = torch.empty(2, dtype=torch.int64, device=dev)
         ms = timed(stream, lambda: ctx.validate_utf8_device(d.data_ptr(), n, d_res.data_ptr()), a.steps)
