@@ -636,7 +636,7 @@ int csvb200_index_shard_info(csvb200_index* idx, csvb200_shard_info* out)
     out->entries = idx->len;
     out->base = idx->ex->rank == 0 ? 0 : 1 + below;
     out->carry_in = (uint32_t)(h_carry[1] & 1u);
-    out->redone = (uint32_t)(h_carry[3] & 1u);
+    out->redone = idx->redone_sticky ? 1u : 0u;
     out->rank = idx->ex->rank;
     out->world = idx->ex->world;
     out->epoch = idx->ex_epoch;
@@ -668,7 +668,7 @@ int csvb200_index_shard_redone(csvb200_index* idx, int* redone, int* carry_parit
     int rc = csvb200_index_sync(idx);
     if (rc) return rc;
     const uint64_t* h_carry = idx->ctx->h_cells + idx->carry_cell * kCellWords;
-    if (redone) *redone = (int)(h_carry[3] & 1u);
+    if (redone) *redone = idx->redone_sticky ? 1 : 0;
     if (carry_parity) *carry_parity = (int)(h_carry[1] & 1u);
     return CSVB200_OK;
 }
@@ -1156,6 +1156,7 @@ int csvb200_index_sync(csvb200_index* idx)
         const uint64_t* h_cell = ctx->h_cells + idx->cell * kCellWords;
         const size_t len = (size_t)(idx->out_base + h_cell[0]);
         idx->end_parity = (int)(h_cell[1] & 1u);
+        if (idx->speculative && idx->verified && (ctx->h_cells[idx->carry_cell * kCellWords + 3] & 1u)) idx->redone_sticky = true;
         if (idx->ex && (ctx->h_cells[idx->carry_cell * kCellWords + 2] >> 63))
             return fail(ctx, CSVB200_ERR_EXCHANGE, "exchange: a lower rank never posted its row for this build (timeout), or lapped the mailbox ring");
         if (len <= idx->cap) {

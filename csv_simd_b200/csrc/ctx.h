@@ -109,6 +109,7 @@ struct csvb200_index {
     uint64_t flag_tile_bytes = 0;
     int any_nonascii = 0;
     uint64_t newlines = 0;                  // CR / LF bytes outside quotes
+    bool redone_sticky = false;             // the misprediction re-index ran (survives a later capacity rebuild)
     csvb200_exchange* ex = nullptr;         // built with the exchange inside the launch (csvb200_index_build_shard_exchange)
     uint64_t ex_epoch = 0;
     size_t carry_cell = SIZE_MAX;

@@ -216,22 +216,24 @@ def segment_layout(counts: Sequence[int]):
 
 
 def gather_segments(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
-    """All ranks' index segments concatenated in rank order, on every rank: ONE all_gather of the segments padded
-    to the longest, then a local compaction.  `local` holds this rank's counts[rank] entries (int64 view of the
-    u64 positions); works on any backend (NCCL over NVLink on the GPUs, gloo in the CPU tests)."""
+    """All ranks' index segments concatenated in rank order, on every rank.  Every segment is broadcast by its owner
+    straight into its final place in the result (one collective per rank, NVLink-rate on NCCL): nothing is padded to
+    the longest segment and nothing is compacted afterwards.  `local` holds this rank's counts[rank] entries (int64
+    view of the u64 positions); works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     counts = [int(c) for c in counts]
     bases, total = segment_layout(counts)
-    width = max(max(counts), 1)
-    padded = torch.zeros(width, dtype=torch.int64, device=local.device)
-    padded[:counts[rank]] = local[:counts[rank]]
-    gathered = torch.empty(world * width, dtype=torch.int64, device=local.device)
-    dist.all_gather_into_tensor(gathered, padded, group=group)
     full = torch.empty(max(total, 1), dtype=torch.int64, device=local.device)
+    if counts[rank]:
+        full[bases[rank]:bases[rank] + counts[rank]].copy_(local[:counts[rank]])
+    works = []
     for k in range(world):
         if counts[k]:
-            full[bases[k]:bases[k] + counts[k]] = gathered[k * width:k * width + counts[k]]
+            src = dist.get_global_rank(group, k) if group is not None else k
+            works.append(dist.broadcast(full[bases[k]:bases[k] + counts[k]], src=src, group=group, async_op=True))
+    for w in works:
+        w.wait()
     return full[:total] if total else full[:0]
 
 
