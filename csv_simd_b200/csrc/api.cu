@@ -82,6 +82,30 @@ int ensure_scratch(csvb200_ctx* ctx, size_t bytes)
     return CSVB200_OK;
 }
 
+int next_build_scratch(csvb200_ctx* ctx, size_t bytes, cudaStream_t stream, uint32_t* tag_out, bool reuse_tag)
+{
+    if (bytes > ctx->bscratch_bytes) {
+        size_t nb = std::max(bytes, ctx->bscratch_bytes * 2);
+        nb = (nb + 4095) & ~size_t(4095);
+        if (ctx->d_bscratch) CU_TRY(ctx, cudaFreeAsync(ctx->d_bscratch, stream));
+        ctx->d_bscratch = nullptr;
+        ctx->bscratch_bytes = 0;
+        CU_TRY(ctx, cudaMallocAsync((void**)&ctx->d_bscratch, nb, stream));
+        ctx->bscratch_bytes = nb;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_bscratch, 0, nb, stream));
+        ctx->desc_tag = 0;
+    }
+    if (!reuse_tag || ctx->desc_tag == 0) {
+        if (ctx->desc_tag >= (uint32_t)kTagMask) {   // the tag wraps after a million launches: one full wipe
+            CU_TRY(ctx, cudaMemsetAsync(ctx->d_bscratch, 0, ctx->bscratch_bytes, stream));
+            ctx->desc_tag = 0;
+        }
+        ctx->desc_tag += 1;
+    }
+    *tag_out = ctx->desc_tag;
+    return CSVB200_OK;
+}
+
 }  // namespace csvb200
 
 namespace {
@@ -139,15 +163,16 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
         h_cell[1] = idx->carry_parity;
     } else {
         const size_t sbytes = 128 + num_tiles * kDescStride * sizeof(uint64_t);
-        int rc = ensure_scratch(ctx, sbytes);
-        if (rc) return rc;
-        // DEBUG (CSVB200_TUNE bit 0x400, timing experiments only): keep the descriptors of the previous build of the
-        // same bytes, so every look-back finds a published prefix on its first poll -- the kernel without its chain
+        // DEBUG (CSVB200_TUNE bit 0x400, timing experiments only): reuse the TAG of the previous build of the same
+        // bytes, so every look-back finds a published prefix on its first poll -- the kernel without its chain
         const bool keep_desc = (ctx->tune & 0x400u) && ctx->dbg_desc_src == idx->src && ctx->dbg_desc_n == n;
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, keep_desc ? 128 : sbytes, ctx->stream));
+        uint32_t tag = 0;
+        int rc = next_build_scratch(ctx, sbytes, ctx->stream, &tag, keep_desc);
+        if (rc) return rc;
         ctx->dbg_desc_src = idx->src;
         ctx->dbg_desc_n = n;
         BuildParams p{};
+        p.desc_tag = tag;
         p.in = idx->src;
         p.n = n;
         p.index = idx->d_index;
@@ -158,8 +183,8 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
         p.carry_count = 0;
         p.carry_parity = idx->carry_parity;
         p.num_tiles = (uint32_t)num_tiles;
-        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
-        p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
+        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_bscratch);
+        p.desc = reinterpret_cast<uint64_t*>(ctx->d_bscratch + 128);
         p.result = d_cell;
         p.result_host = ctx->host_result ? h_cell : nullptr;
         p.write_sentinel = idx->out_base == 1 ? 1u : 0u;
@@ -182,9 +207,10 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             idx->flag_tile_bytes = build_flag_tile_bytes(n, use_tma, ctx->tune);
             p.validate = 1u;
             p.nonascii_bitmap = idx->d_nonascii;
-            p.nl_out = reinterpret_cast<unsigned long long*>(ctx->d_scratch + 16);
-            p.hi_out = reinterpret_cast<uint32_t*>(ctx->d_scratch + 24);
-            p.ex_done = reinterpret_cast<uint32_t*>(ctx->d_scratch + 4);
+            p.nl_out = reinterpret_cast<unsigned long long*>(ctx->d_bscratch + 16);
+            p.hi_out = reinterpret_cast<uint32_t*>(ctx->d_bscratch + 24);
+            p.ex_done = reinterpret_cast<uint32_t*>(ctx->d_bscratch + 4);
+            p.scratch_totals = 1u;
         }
         if (idx->speculative) {
             uint64_t* d_carry = ctx->d_cells + idx->carry_cell * kCellWords;
@@ -195,8 +221,9 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             } else if (idx->ex) {
                 // exchange inside the launch: separator total and the "look-back role over" counter live in the
                 // zeroed head of the scratch; the last CTA posts the row and resolves the carry chain into d_carry
-                p.total_out = reinterpret_cast<unsigned long long*>(ctx->d_scratch + 8);
-                p.ex_done = reinterpret_cast<uint32_t*>(ctx->d_scratch + 4);
+                p.total_out = reinterpret_cast<unsigned long long*>(ctx->d_bscratch + 8);
+                p.ex_done = reinterpret_cast<uint32_t*>(ctx->d_bscratch + 4);
+                p.scratch_totals = 1u;
                 p.ex.peers = idx->ex->d_peers;
                 p.ex.rank = idx->ex->rank;
                 p.ex.world = idx->ex->world;
@@ -477,6 +504,7 @@ void csvb200_ctx_destroy(csvb200_ctx* ctx)
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_bscratch) cudaFree(ctx->d_bscratch);
     if (ctx->d_cells) cudaFree(ctx->d_cells);
     if (ctx->h_cells) cudaFreeHost(ctx->h_cells);
     delete ctx->pool;
@@ -805,10 +833,11 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
         }
         const uint64_t num_tiles = std::max<uint64_t>(1, (len + kTileBytes - 1) / kTileBytes);   // an empty shard runs one empty tile
         const size_t sbytes = 128 + num_tiles * kDescStride * sizeof(uint64_t);
-        rc = ensure_scratch(ctx, sbytes);
+        uint32_t tag = 0;
+        rc = next_build_scratch(ctx, sbytes, s_up, &tag);
         if (rc) break;
-        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_scratch, 0, sbytes, s_up);
         BuildParams p{};
+        p.desc_tag = tag;
         p.in = d_bytes + off;
         p.n = len;
         p.index = d_index;
@@ -817,8 +846,8 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
         p.pos_bias = o.pos_bias + off;
         p.carry = d_cells + c * kCellWords;
         p.num_tiles = (uint32_t)num_tiles;
-        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
-        p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
+        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_bscratch);
+        p.desc = reinterpret_cast<uint64_t*>(ctx->d_bscratch + 128);
         p.result = d_cells + (c + 1) * kCellWords;
         p.result_host = ctx->host_result ? h_cells + (c + 1) * kCellWords : nullptr;
         p.write_sentinel = (c == 0 && out_base) ? 1u : 0u;

@@ -31,8 +31,13 @@ struct csvb200_ctx {
     cudaStream_t stream = nullptr;       // the stream work is issued on
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
     bool timed = false;
-    uint8_t* d_scratch = nullptr;  // [16 B ticket cell][look-back descriptors]
+    uint8_t* d_scratch = nullptr;  // generic scratch (materialisation): zeroed by its users
     size_t scratch_bytes = 0;
+    // scratch of the index builds: [128 B head: ticket, done counter, totals][tagged look-back descriptors]; zeroed when
+    // it is (re)allocated and when the 20-bit tag wraps, never between launches
+    uint8_t* d_bscratch = nullptr;
+    size_t bscratch_bytes = 0;
+    uint32_t desc_tag = 0;
     uint64_t* d_cells = nullptr;
     uint64_t* h_cells = nullptr;
     // ownership of the result cells: every live index object, shard job and running pipeline holds its cells
@@ -144,6 +149,8 @@ struct CellLease {
     bool ok() const { return first != SIZE_MAX; }
 };
 int ensure_scratch(csvb200_ctx* ctx, size_t bytes);
+// build scratch of at least `bytes` + a fresh descriptor tag for one launch on `stream`
+int next_build_scratch(csvb200_ctx* ctx, size_t bytes, cudaStream_t stream, uint32_t* tag_out, bool reuse_tag = false);
 bool is_pinned(const void* p);
 SlicePool& io_pool(csvb200_ctx* ctx);   // the context's host-thread pool (CSVB200_IO_THREADS)
 // host -> device copy of n bytes on the context's stream; pinned sources go straight to cudaMemcpyAsync,

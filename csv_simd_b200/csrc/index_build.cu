@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
 
     if (p.run_flag != nullptr && *p.run_flag == 0u) return;   // conditional redo that is not needed
     // dynamic tile id: a tile only ever waits on tiles whose CTAs already started
-    if (tid == 0) sm.tile = atomicAdd(p.ticket, 1u);
+    if (tid == 0) {
+        sm.tile = atomicAdd(p.ticket, 1u);
+        if (sm.tile == p.num_tiles - 1u) *p.ticket = 0u;   // the last ticket: back to zero for the next launch
+    }
     __syncthreads();
     const uint32_t tile = sm.tile;
     const uint64_t tile_off = (uint64_t)tile * kTileBytes;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
         }
         // (par, o0, o1) is the tile aggregate
         if (lane == 0)
-            st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride, kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
+            st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride, kStatusAgg | ((uint64_t)p.desc_tag << kTagShift) | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
 
         uint32_t pin;
         uint64_t base;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 3) index_build_kernel(const BuildPar
         if (lane == 0) {
             const uint32_t pend = pin ^ par;
             const uint64_t cend = base + (pin ? o1 : o0);
-            st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride, kStatusPrefix | (pend ? kParityBit : 0ull) | (cend & kCountMask));
+            st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride, kStatusPrefix | ((uint64_t)p.desc_tag << kTagShift) | (pend ? kParityBit : 0ull) | (cend & kCountMask));
             sm.pin = pin;
             sm.base = base;
             sm.tot0 = o0;

@@ -316,6 +316,9 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 // 0.418 ms: a ticket held for a whole super-tile period before its loads start delays the
                 // look-back of every later tile.)
                 uint32_t tile = atomicAdd(p.ticket, 1u);
+                // every CTA takes tickets until it draws an invalid one: num_tiles + grid in all; the last one drawn
+                // puts the counter back to zero for the next launch on this scratch
+                if (tile == p.num_tiles + gridDim.x - 1u) *p.ticket = 0u;
                 if (tile >= p.num_tiles) tile = kInvalidTile;
 #pragma unroll
                 for (int sub = 0; sub < kSub; ++sub) {
@@ -380,7 +383,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             }
             if (lane == 0)
                 st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride,
-                               kStatusAgg | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
+                               kStatusAgg | ((uint64_t)p.desc_tag << kTagShift) | (par ? kParityBit : 0ull) | (uint64_t)o0 | ((uint64_t)o1 << 20));
             uint32_t pin;
             uint64_t base;
             // one 32-descriptor window per round trip (wider windows measured slower both rounds: 0.400 / 0.427 ms
@@ -390,7 +393,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 const uint32_t pend = pin ^ par;
                 const uint64_t cend = base + (pin ? o1 : o0);
                 st_relaxed_u64(p.desc + (uint64_t)tile * kDescStride,
-                               kStatusPrefix | (pend ? kParityBit : 0ull) | (cend & kCountMask));
+                               kStatusPrefix | ((uint64_t)p.desc_tag << kTagShift) | (pend ? kParityBit : 0ull) | (cend & kCountMask));
 #pragma unroll
                 for (int sub = 0; sub < kSub; ++sub) {
                     const uint64_t b0 = base + (pin ? sub_o1[sub] : sub_o0[sub]);

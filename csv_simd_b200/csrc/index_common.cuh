@@ -129,7 +129,7 @@ __device__ __forceinline__ uint64_t virtual_prefix_desc(const BuildParams& p)
         carry_parity = 0u;
         for (uint32_t j = 0; j < p.shard_rank; ++j) carry_parity ^= p.shard_par[j] & 1u;
     }
-    return kStatusPrefix | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
+    return kStatusPrefix | ((uint64_t)p.desc_tag << kTagShift) | (carry_parity ? kParityBit : 0ull) | (carry_count & kCountMask);
 }
 
 // Called by the thread that resolved the LAST tile of a launch: entries emitted through the end of the
@@ -169,9 +169,16 @@ __device__ __forceinline__ void exchange_if_last(const BuildParams& p)
             p.result_host[3] = nl;
         }
     }
+    const uint64_t total = p.total_out != nullptr ? ld_volatile_u64(reinterpret_cast<const uint64_t*>(p.total_out)) : 0ull;
+    // this CTA is the last user of the counters in the scratch head: zero for the next launch (there is no memset)
+    *p.ex_done = 0u;
+    if (p.scratch_totals) {
+        if (p.total_out != nullptr) *p.total_out = 0ull;
+        if (p.nl_out != nullptr) *p.nl_out = 0ull;
+        if (p.hi_out != nullptr) *p.hi_out = 0u;
+    }
     if (p.ex.peers == nullptr) return;
     const uint64_t entries = ld_volatile_u64(p.result + 0), endp = ld_volatile_u64(p.result + 1);
-    const uint64_t total = p.total_out != nullptr ? ld_volatile_u64(reinterpret_cast<const uint64_t*>(p.total_out)) : 0ull;
     const uint64_t used = (virtual_prefix_desc(p) >> 61) & 1ull;
     exchange_post_and_resolve(p.ex, entries, endp, used, total);
 }
@@ -207,6 +214,7 @@ __device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_
         for (int j = 0; j < kLookbackPerLane; ++j) {
             const int64_t idx = idx0 - (int64_t)lane * kLookbackPerLane - j;
             d[j] = idx >= 0 ? ld_relaxed_u64(p.desc + idx * kDescStride) : virtual_prefix();
+            if (((d[j] >> kTagShift) & kTagMask) != (uint64_t)p.desc_tag) d[j] = 0ull;   // another launch's word: not ready
         }
         // lane-local fold, nearest tile first: L <- agg(t_j) o L
         uint32_t lp_ = 0u, l0 = 0u, l1 = 0u;   // lane composite (parity, c0, c1)

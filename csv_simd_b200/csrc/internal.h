@@ -15,9 +15,13 @@ constexpr int kWarps = kThreads / 32;
 // ---- look-back descriptor (one u64 per tile, written/read as a single word) --
 //   [63:62] status   0 = not ready, 1 = tile aggregate, 2 = inclusive prefix
 //   [61]    parity   aggregate: quote parity of the tile; prefix: absolute parity at tile end
+//   [60:41] tag      of the launch that wrote the word (BuildParams::desc_tag, 1 .. 2^20 - 1): a descriptor whose tag is
+//                    not the reader's own launch reads as "not ready", so the scratch is NOT zeroed between launches
+//                    (round 1 memset 2 MiB per GiB of input in front of every launch); the ticket and the counters in
+//                    the head of the scratch are put back to zero by the last CTA that touches them
 //   aggregate: [19:0] c0 = unquoted separators if the tile is entered outside quotes
 //              [39:20] c1 = same if entered inside quotes
-//   prefix:    [60:0] absolute number of index entries emitted up to the tile end
+//   prefix:    [40:0] absolute number of index entries emitted up to the tile end (2.2e12: an 8 TB index)
 // Each descriptor sits alone in a 128-byte line: every resident CTA polls the descriptors of the
 // same few hundred predecessor tiles, and packed (8-byte stride) descriptors put all of that
 // traffic on a handful of L2 slices (measured: 5x slower with a 320-tile window).  One line per
@@ -26,7 +30,9 @@ constexpr uint64_t kDescStride = 16;  // in u64 words
 constexpr uint64_t kStatusAgg = 1ull << 62;
 constexpr uint64_t kStatusPrefix = 2ull << 62;
 constexpr uint64_t kParityBit = 1ull << 61;
-constexpr uint64_t kCountMask = (1ull << 61) - 1;
+constexpr int kTagShift = 41;
+constexpr uint64_t kTagMask = 0xfffffull;
+constexpr uint64_t kCountMask = (1ull << kTagShift) - 1;
 
 // ---- cross-GPU exchange over peer-mapped mailboxes (NVLink P2P stores; no collective library) ----------------
 // Every rank owns a mailbox in its own HBM: kExRing slots (one per build, epoch % kExRing) of kExMaxWorld rows of
@@ -64,8 +70,10 @@ struct BuildParams {
     uint64_t carry_count;    // entries emitted by earlier launches of the same build
     uint32_t carry_parity;   // quote parity entering byte 0 of `in`
     uint32_t num_tiles;
-    uint64_t* desc;          // [num_tiles] look-back descriptors, zeroed before launch
-    uint32_t* ticket;        // dynamic tile counter, zeroed before launch
+    uint64_t* desc;          // [num_tiles] look-back descriptors (tagged, never zeroed between launches)
+    uint32_t desc_tag;       // this launch's tag
+    uint32_t scratch_totals; // total_out / nl_out / hi_out live in the scratch head: the last CTA resets them after use
+    uint32_t* ticket;        // dynamic tile counter; zero at launch, reset by the CTA that takes the last ticket
     uint64_t* result;        // {entries emitted through the end of this launch, end parity}
     uint64_t* result_host;   // optional pinned (UVA-mapped) host mirror of `result`: written straight over PCIe, no D2H copy node
     uint32_t write_sentinel; // the CTA of tile 0 writes index[0] = 0 (src/reader.rs:216) instead of a separate memset

@@ -128,9 +128,9 @@ struct Pipeline {
         const bool use_tma = tma_path_usable(s.bytes) && ctx->kernel_override != 1;
         const uint64_t num_tiles = (s.bytes + kTileBytes - 1) / kTileBytes;
         const size_t sbytes = 128 + num_tiles * kDescStride * sizeof(uint64_t);
-        int rc = ensure_scratch(ctx, sbytes);
+        uint32_t tag = 0;
+        int rc = next_build_scratch(ctx, sbytes, st, &tag);
         if (rc) return rc;
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, st));
         BuildParams p{};
         p.in = s.d_in;
         p.n = s.bytes;
@@ -141,8 +141,9 @@ struct Pipeline {
         p.carry = ctx->d_cells + prev_cell * kCellWords;
         p.carry_parity_only = 1;
         p.num_tiles = (uint32_t)num_tiles;
-        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_scratch);
-        p.desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
+        p.desc_tag = tag;
+        p.ticket = reinterpret_cast<uint32_t*>(ctx->d_bscratch);
+        p.desc = reinterpret_cast<uint64_t*>(ctx->d_bscratch + 128);
         p.result = ctx->d_cells + s.cell * kCellWords;
         p.result_host = ctx->host_result ? ctx->h_cells + s.cell * kCellWords : nullptr;
         p.write_sentinel = c == 0 ? 1u : 0u;     // sentinel (src/reader.rs:216)
