@@ -103,6 +103,7 @@ struct __align__(1024) SmemTma {
     uint64_t empty[S::kSlots];              // workers -> producer
     uint64_t agg_full[S::kRing];               // workers -> look-back warp
     uint64_t pref_full[S::kRing];              // look-back warp -> workers
+    uint64_t go;                               // workers -> producer: "half way through this iteration's compaction"
     uint32_t tile_id[S::kSlots];            // super-tile id of the part in each slot
     uint32_t agg_tile[S::kRing];
     uint32_t warp_agg[S::kRing][S::kSub][S::kWorkers];
@@ -264,15 +265,19 @@ __device__ __forceinline__ void compact_sub(SmemTma<S>& sm, const BuildParams& p
 }
 
 // compaction of the `it`-th super-tile this CTA processed
+// signal_go: arrive on the producer's `go` barrier after the first sub-tile (see the producer)
 template <class S>
 __device__ __forceinline__ void compact_super(SmemTma<S>& sm, const BuildParams& p, const SuperRegs<S::kSub>& t, uint32_t it,
-                                              uint32_t tid, uint32_t warp)
+                                              uint32_t tid, uint32_t warp, bool signal_go)
 {
     const uint32_t pb = it % S::kRing;
     mbar_wait(&sm.pref_full[pb], (it / S::kRing) & 1u);
     const PrefixInfo<S::kSub, S::kWorkers>& pi = sm.pref[pb];
 #pragma unroll
-    for (int sub = 0; sub < S::kSub; ++sub) compact_sub<S>(sm, p, t.sub[sub], pi, sub, t.tile, it * S::kSub + sub, tid, warp);
+    for (int sub = 0; sub < S::kSub; ++sub) {
+        compact_sub<S>(sm, p, t.sub[sub], pi, sub, t.tile, it * S::kSub + sub, tid, warp);
+        if (sub == 0 && signal_go && (tid & 31u) == 0u) mbar_arrive(&sm.go);
+    }
 }
 
 // kVal: CSVB200_BUILD_VALIDATE by-products; kEx: the cross-GPU exchange in the epilogue of the last CTA.  Both are
@@ -288,6 +293,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
     constexpr int kSub = S::kSub, kSkew = S::kSkew, kRing = S::kRing, kWorkerWarps = S::kWorkers;
+    const bool jit = (p.tune & 4u) == 0u;   // CSVB200_TUNE bit 4: draw tickets as soon as a ring slot frees (round 1; A/B)
 
     if (p.run_flag != nullptr && *p.run_flag == 0u) return;   // conditional redo that is not needed
 
@@ -302,6 +308,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             mbar_init(&sm.agg_full[i], kWorkerWarps);
             mbar_init(&sm.pref_full[i], 1);
         }
+        mbar_init(&sm.go, kWorkerWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -311,6 +318,12 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
             for (uint32_t it = 0;; ++it) {
+                // Just-in-time ticket: the ticket of super-tile `it` is drawn when the workers are half way through the
+                // compaction that precedes its classification (one sub-tile compaction ~ the TMA latency), not as soon
+                // as a ring slot frees.  A ticket held for a whole period before its tile is classified makes every
+                // later tile wait for an aggregate that is a period away -- and a CTA that waits for its prefix holds
+                // such a ticket the whole time it waits.
+                if (jit && it > 0u) mbar_wait(&sm.go, (it - 1u) & 1u);
                 // dynamic super-tile id: a tile only ever waits on tiles whose CTAs already hold a ticket.
                 // (Taking the NEXT ticket early to hide the atomic's round trip measured slower, 0.423 vs
                 // 0.418 ms: a ticket held for a whole super-tile period before its loads start delays the
@@ -541,12 +554,15 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
 
             // ---- ordered compaction of the super-tile classified kSkew iterations ago: its look-back has
             //      had kSkew classify phases to complete ----
-            if (pend[0].tile != kInvalidTile) compact_super<S>(sm, p, pend[0], it - kSkew, tid, warp);
+            if (pend[0].tile != kInvalidTile)
+                compact_super<S>(sm, p, pend[0], it - kSkew, tid, warp, jit);
+            else if (jit && lane == 0u)
+                mbar_arrive(&sm.go);   // nothing to compact yet: the producer may draw the next ticket at once
             if (cur.tile == kInvalidTile) {
                 // drain: the younger pending super-tiles, oldest first
 #pragma unroll
                 for (int k = 1; k < kSkew; ++k)
-                    if (pend[k].tile != kInvalidTile) compact_super<S>(sm, p, pend[k], it - kSkew + k, tid, warp);
+                    if (pend[k].tile != kInvalidTile) compact_super<S>(sm, p, pend[k], it - kSkew + k, tid, warp, false);
                 break;
             }
 #pragma unroll
