@@ -247,6 +247,29 @@ inline StructureIndex read(const Mmap& memmap, Gpu& gpu = Gpu::instance())
           gpu.raw());
     return StructureIndex(gpu.raw(), h);
 }
+
+// The same over several GPUs of this process: ONE byte slice in, ONE Vec<usize>-shaped index out
+// (csvb200_multi_index_build_to_host: the slice is cut "without first knowing record breaks", README.md:24, the
+// 32-byte rows cross NVLink from inside the build launches).  What `create` (src/lib.rs:61-74) would call at 8 GPUs.
+inline std::vector<uint64_t> read_multi(const Mmap& memmap, const std::vector<int>& devices)
+{
+    if (memmap.len() < 64) throw StructureError(ErrorKind::ReferencePanic, "n < 64: the reference panics on this input");
+    csvb200_multi* m = nullptr;
+    if (csvb200_multi_create(devices.data(), static_cast<int>(devices.size()), &m) != CSVB200_OK)
+        throw StructureError(ErrorKind::Gpu, "csvb200_multi_create failed");
+    std::vector<uint64_t> out(memmap.len() / 3 + 4096);
+    size_t len = 0;
+    int rc = csvb200_multi_index_build_to_host(m, memmap.data(), memmap.len(), nullptr, out.data(), out.size(), &len);
+    if (rc == CSVB200_ERR_CAPACITY && len > out.size()) {   // denser than the first guess: the exact size is reported
+        out.resize(len);
+        rc = csvb200_multi_index_build_to_host(m, memmap.data(), memmap.len(), nullptr, out.data(), out.size(), &len);
+    }
+    const std::string why = rc ? csvb200_multi_last_error(m) : "";
+    csvb200_multi_destroy(m);
+    if (rc != CSVB200_OK) throw StructureError(ErrorKind::Gpu, why);
+    out.resize(len);
+    return out;
+}
 }  // namespace reader
 
 // ---- src/tape.rs:281-284, 385-428 -------------------------------------------------------------------

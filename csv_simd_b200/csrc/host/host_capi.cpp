@@ -48,6 +48,21 @@ extern "C" {
 
 const char* csvsimd_last_error() { return g_err.c_str(); }
 
+// reader::read_multi on a file: returns the entry count; dst may be NULL to size the destination
+int csvsimd_read_multi(const char* filename, const int* devices, int ndev, uint64_t* dst, size_t cap, size_t* len_out)
+{
+    return guard([&] {
+        const Mmap mm = Mmap::map(filename);
+        const std::vector<int> devs(devices, devices + ndev);
+        const std::vector<uint64_t> idx = reader::read_multi(mm, devs);
+        *len_out = idx.size();
+        if (dst) {
+            if (idx.size() > cap) throw std::out_of_range("destination too small");
+            std::memcpy(dst, idx.data(), idx.size() * sizeof(uint64_t));
+        }
+    });
+}
+
 int csvsimd_create(const char* filename, void** tape_out)
 {
     return guard([&] { *tape_out = new Tape(create(filename)); });

@@ -265,18 +265,20 @@ __device__ __forceinline__ void compact_sub(SmemTma<S>& sm, const BuildParams& p
 }
 
 // compaction of the `it`-th super-tile this CTA processed
-// signal_go: arrive on the producer's `go` barrier after the first sub-tile (see the producer)
+// go_at: where this warp arrives on the producer's `go` barrier (see the producer): 0 = nowhere, 1 = as soon as the
+// prefix is there, 2 = after the first sub-tile's compaction, 3 = after the last one
 template <class S>
 __device__ __forceinline__ void compact_super(SmemTma<S>& sm, const BuildParams& p, const SuperRegs<S::kSub>& t, uint32_t it,
-                                              uint32_t tid, uint32_t warp, bool signal_go)
+                                              uint32_t tid, uint32_t warp, uint32_t go_at)
 {
     const uint32_t pb = it % S::kRing;
     mbar_wait(&sm.pref_full[pb], (it / S::kRing) & 1u);
+    if (go_at == 1u && (tid & 31u) == 0u) mbar_arrive(&sm.go);
     const PrefixInfo<S::kSub, S::kWorkers>& pi = sm.pref[pb];
 #pragma unroll
     for (int sub = 0; sub < S::kSub; ++sub) {
         compact_sub<S>(sm, p, t.sub[sub], pi, sub, t.tile, it * S::kSub + sub, tid, warp);
-        if (sub == 0 && signal_go && (tid & 31u) == 0u) mbar_arrive(&sm.go);
+        if (((sub == 0 && go_at == 2u) || (sub == S::kSub - 1 && go_at == 3u)) && (tid & 31u) == 0u) mbar_arrive(&sm.go);
     }
 }
 
@@ -294,6 +296,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
     const uint32_t warp = tid >> 5;
     constexpr int kSub = S::kSub, kSkew = S::kSkew, kRing = S::kRing, kWorkerWarps = S::kWorkers;
     const bool jit = (p.tune & 4u) == 0u;   // CSVB200_TUNE bit 4: draw tickets as soon as a ring slot frees (round 1; A/B)
+    const uint32_t go_at = !jit ? 0u : ((p.tune >> 3) & 3u) == 1u ? 1u : ((p.tune >> 3) & 3u) == 2u ? 3u : 2u;   // A/B: bits 8, 16
 
     if (p.run_flag != nullptr && *p.run_flag == 0u) return;   // conditional redo that is not needed
 
@@ -555,14 +558,14 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             // ---- ordered compaction of the super-tile classified kSkew iterations ago: its look-back has
             //      had kSkew classify phases to complete ----
             if (pend[0].tile != kInvalidTile)
-                compact_super<S>(sm, p, pend[0], it - kSkew, tid, warp, jit);
+                compact_super<S>(sm, p, pend[0], it - kSkew, tid, warp, go_at);
             else if (jit && lane == 0u)
                 mbar_arrive(&sm.go);   // nothing to compact yet: the producer may draw the next ticket at once
             if (cur.tile == kInvalidTile) {
                 // drain: the younger pending super-tiles, oldest first
 #pragma unroll
                 for (int k = 1; k < kSkew; ++k)
-                    if (pend[k].tile != kInvalidTile) compact_super<S>(sm, p, pend[k], it - kSkew + k, tid, warp, false);
+                    if (pend[k].tile != kInvalidTile) compact_super<S>(sm, p, pend[k], it - kSkew + k, tid, warp, 0u);
                 break;
             }
 #pragma unroll

@@ -67,8 +67,47 @@ def main():
         d_res = torch.empty(2, dtype=torch.int64, device=dev)
         ctx.validate_utf8_device(d.data_ptr(), n, d_res.data_ptr())
         torch.cuda.synchronize()
+        # round 2: several columns in one sweep; the build with its by-products + the flagged-tile UTF-8 pass
+        cols = [1, 5, 9, 13]
+        d_offs = [torch.empty(nrec + 1, dtype=torch.int64, device=dev) for _ in cols]
+        idx.materialize_columns_device(cols, 0, nrec, 3, [t.data_ptr() for t in d_offs])
+        torch.cuda.synchronize()
+        totals = [int(t[-1].item()) for t in d_offs]
+        d_vals = [torch.empty(max(t, 1), dtype=torch.uint8, device=dev) for t in totals]
+        idx.materialize_columns_device(cols, 0, nrec, 3, [t.data_ptr() for t in d_offs], [t.data_ptr() for t in d_vals], totals)
+        dv = d.clone()
+        dv[n // 3:n // 3 + 4] = torch.tensor([0xF0, 0x9F, 0x99, 0x82], dtype=torch.uint8, device=dev)   # one emoji: one flagged tile
+        iv = ctx.index_build_device(dv.data_ptr(), n, cs.BUILD_VALIDATE)
+        iv.validation()
+        iv.validate_utf8()
+        iv.free()
+        # round 2: the exchange inside the launch (two ranks emulated in rank order on this GPU) and the lookups over
+        # a distributed index (segments on "two devices" = this GPU twice)
+        c2 = [cs.Context(0), cs.Context(0)]
+        e2 = [c.exchange(k, 2) for k, c in enumerate(c2)]
+        cs.Exchange.connect_local(e2)
+        xa = c2[0].index_build_shard_exchange(e2[0], d.data_ptr(), half, 0)
+        xa.sync()
+        xb = c2[1].index_build_shard_exchange(e2[1], tail.data_ptr(), n - half, half)
+        assert len(xa) + len(xb) == E
+        xa.free()
+        xb.free()
+        for e in e2:
+            e.close()
+        for c in c2:
+            c.close()
         idx.free()
         print(f"{wl}: n={n} E={E} ok")
+    m = cs.Multi([0, 0])
+    mi = m.index_build_distributed(data[:64 << 20])
+    try:
+        mi.tape_init(16, True)      # the prefix ends mid-row: InvalidCsvFormat is reported AFTER the metadata is set
+    except cs.InvalidCsvFormat:
+        pass
+    rec, fld = gen.queries(1_000_000, 100000, 16, seed=46)
+    mi.seek_fields(rec, fld)
+    mi.free()
+    m.close()
     # K1 known-answer exports on a small input
     small = data[:1 << 20]
     ctx.block_masks(small)
