@@ -79,6 +79,10 @@ using ShapeH = TmaShape<2, 1, 7680, 2, 1, 12>;   // 2 CTAs / SM x 12 worker warp
 //   kSkew = 2: 0.391 / 0.347 at 2 CTAs, 0.423 / 0.366 at 3 (spills);  1 CTA x 16 worker warps: 0.436 / 0.367
 //   look-back windows of 64 / 128 descriptors: 0.401 / 0.351 and 0.427 / 0.372;  re-polling one descriptor instead
 //   of the window: no change.
+// Just-in-time tickets (the producer draws the ticket of the next super-tile when the workers are half way through the
+// compaction before it, not when a ring slot frees): B 0.374 / 0.337 (0.96 / 0.72 of the copy peak), A unchanged;
+// signalled right after the prefix wait instead 0.377 / 0.341, after the whole compaction 0.402 / 0.351.  On top of it:
+// no skew (compaction right after classification) 0.437 / 0.395; one 32 KiB sub-tile per descriptor 0.449 / 0.384.
 // With every look-back answered on its first poll (the descriptors of a previous build of the same bytes left in place:
 // CSVB200_TUNE bit 0x400, a timing experiment) B runs 0.363 / 0.306 ms: the chain costs 7 % / 11 %, it is the
 // workers waiting for their prefix (ncu: 11.7 % of the samples on that wait against 1.2 %), and none of the above
@@ -446,9 +450,9 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
         const uint64_t full_rows = p.n >> 7;
         const uint32_t tail = (uint32_t)(p.n & 127u);
         // masks of the super-tiles that are classified but not yet compacted (kSkew of them, oldest first)
-        SuperRegs<kSub> pend[kSkew];
+        SuperRegs<kSub> pend[kSkew > 0 ? kSkew : 1];
 #pragma unroll
-        for (int k = 0; k < kSkew; ++k) pend[k].tile = kInvalidTile;
+        for (int k = 0; k < (kSkew > 0 ? kSkew : 1); ++k) pend[k].tile = kInvalidTile;
 
         for (uint32_t it = 0;; ++it) {
             const uint32_t b = it % kRing;
@@ -555,6 +559,13 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 mbar_arrive(&sm.agg_full[b]);
             }
 
+            if (kSkew == 0) {
+                // no skew: the tile just classified is compacted at once (the other CTAs of the SM cover the look-back);
+                // nothing outlives an iteration, which frees the registers the pending masks take
+                if (cur.tile == kInvalidTile) break;
+                compact_super<S>(sm, p, cur, it, tid, warp, go_at);
+                continue;
+            }
             // ---- ordered compaction of the super-tile classified kSkew iterations ago: its look-back has
             //      had kSkew classify phases to complete ----
             if (pend[0].tile != kInvalidTile)
@@ -570,7 +581,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             }
 #pragma unroll
             for (int k = 0; k + 1 < kSkew; ++k) pend[k] = pend[k + 1];
-            pend[kSkew - 1] = cur;
+            pend[kSkew > 0 ? kSkew - 1 : 0] = cur;
         }
     }
 }
