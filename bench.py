@@ -439,6 +439,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 redone_any.append(rank)
             return ln_
 
+        barrier()   # page-locking the buffers above takes a different time on every rank: line the ranks up first
         for _ in range(2):
             step_e2e()
         barrier()

@@ -82,7 +82,7 @@ struct csvb200_exchange {
     bool ipc_opened[csvb200::kExMaxWorld] = {};
     uint64_t** d_peers = nullptr;                        // device copy of peer[]
     bool connected = false;
-    uint64_t timeout_ns = 2000000000ull;                 // CSVB200_EXCHANGE_TIMEOUT_MS
+    uint64_t timeout_ns = 5000000000ull;                 // CSVB200_EXCHANGE_TIMEOUT_MS (default 5 s)
     uint64_t* d_row4 = nullptr;                          // {entries, end parity, carry used, total} of an end-to-end build
     uint64_t* h_rows = nullptr;                          // pinned: one mailbox slot (host-side wait for all ranks)
 };

@@ -194,7 +194,7 @@ void csvb200_shard_job_free(csvb200_shard_job* job);
  * ranks only, derives its true carry-in, the entries before its segment and whether its guess was wrong, and leaves
  * them where the conditional redo launch and the host find them.  No NCCL, no host round trip, no extra launch; a
  * rank that never posts is reported as CSVB200_ERR_EXCHANGE after a timeout (CSVB200_EXCHANGE_TIMEOUT_MS, default
- * 2000) instead of hanging the GPU.  Builds through an exchange are COLLECTIVE: every rank issues them in the same
+ * 5000) instead of hanging the GPU.  Builds through an exchange are COLLECTIVE: every rank issues them in the same
  * order.  At most 16 ranks; at most 1024 builds may be in flight ahead of the slowest rank (detected, not silent).
  *
  * Wiring: create one endpoint per context, hand every rank's 64-byte handle to every other rank by any means (the
