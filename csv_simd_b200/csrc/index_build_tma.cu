@@ -83,6 +83,9 @@ using ShapeH = TmaShape<2, 1, 7680, 2, 1, 12>;   // 2 CTAs / SM x 12 worker warp
 // compaction before it, not when a ring slot frees): B 0.374 / 0.337 (0.96 / 0.72 of the copy peak), A unchanged;
 // signalled right after the prefix wait instead 0.377 / 0.341, after the whole compaction 0.402 / 0.351.  On top of it:
 // no skew (compaction right after classification) 0.437 / 0.395; one 32 KiB sub-tile per descriptor 0.449 / 0.384.
+// Two instruction-level variants on top of that changed nothing on cfg3 (kv12): the copy-out with one 32-bit add per
+// entry (0.336 vs 0.336 ms; 0.388 vs 0.379 on cfg2) and the transpose's right shifts issued to the FMA pipe through
+// __umulhi (0.337 vs 0.336) -- the quote-heavy case is not bound by the ALU pipe or by the copy-out's instruction count.
 // With every look-back answered on its first poll (the descriptors of a previous build of the same bytes left in place:
 // CSVB200_TUNE bit 0x400, a timing experiment) B runs 0.363 / 0.306 ms: the chain costs 7 % / 11 %, it is the
 // workers waiting for their prefix (ncu: 11.7 % of the samples on that wait against 1.2 %), and none of the above
