@@ -9,7 +9,7 @@ SHAPES = {0x1000: "A: 2 CTAs/SM, 95 regs, 2 staging buffers (round 1)", 0x2000: 
           0x3000: "D: A with 128 KiB per descriptor (kSub=4)", 0x4000: "E: B with kSub=4 (spills)",
           0x5000: "F: B with 2 super-tiles of skew (spills)", 0x6000: "G: A with 2 super-tiles of skew",
           0x7000: "H: 2 CTAs/SM x 12 worker warps (96 KiB per descriptor)", 0x8000: "I: 1 CTA/SM x 16 worker warps (128 KiB per descriptor)",
-          0x9000: "J: B without skew", 0xA000: "K: B with 32 KiB per descriptor (kSub=1)", 0xB000: "L: K without skew", 0: "default (B)"}
+          0x9000: "J: B without skew", 0xC000: "M: B with the transpose's right shifts on the FMA pipe (__umulhi)", 0xA000: "K: B with 32 KiB per descriptor (kSub=1)", 0xB000: "L: K without skew", 0: "default (B)"}
 
 
 def label(run: int, t: int) -> str:
@@ -26,6 +26,8 @@ def label(run: int, t: int) -> str:
             nm += ", go right after the prefix wait"
         if (m & 24) == 16:
             nm += ", go after the whole compaction"
+        if m & 32:
+            nm += ", copy-out with one 32-bit add per entry"
     if m & 0x400:
         nm += " + NO CHAIN (timing experiment: every look-back answered on its first poll)"
     return nm
