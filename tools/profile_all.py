@@ -39,13 +39,15 @@ def main():
         ctx.shard_quote_parity_device(d.data_ptr(), n, par.data_ptr())
         res = torch.zeros((2, 4), dtype=torch.int64, device=dev)
         half = (n // 2) | 5
-        a = ctx.index_build_shard_speculative(d.data_ptr(), half, 0, 0, True, res[0].data_ptr())
         tail = d[half:half + (n - half)].clone()
+        torch.cuda.synchronize()   # torch's stream and the context's own (non-blocking) stream are not ordered otherwise
+        a = ctx.index_build_shard_speculative(d.data_ptr(), half, 0, 0, True, res[0].data_ptr())
         b = ctx.index_build_shard_speculative(tail.data_ptr(), n - half, 1, half, False, res[1].data_ptr())
         fin = torch.zeros((2, 2), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
         a.shard_verify(res.data_ptr(), 2, fin.data_ptr())
         b.shard_verify(res.data_ptr(), 2, fin.data_ptr())
-        assert len(a) + len(b) == E
+        assert len(a) + len(b) == E, (len(a), len(b), E, res.tolist(), fin.tolist(), a.shard_redone(), b.shard_redone())
         a.free()
         b.free()
         # K4 lookups + byte gather
@@ -77,6 +79,7 @@ def main():
         idx.materialize_columns_device(cols, 0, nrec, 3, [t.data_ptr() for t in d_offs], [t.data_ptr() for t in d_vals], totals)
         dv = d.clone()
         dv[n // 3:n // 3 + 4] = torch.tensor([0xF0, 0x9F, 0x99, 0x82], dtype=torch.uint8, device=dev)   # one emoji: one flagged tile
+        torch.cuda.synchronize()
         iv = ctx.index_build_device(dv.data_ptr(), n, cs.BUILD_VALIDATE)
         iv.validation()
         iv.validate_utf8()
