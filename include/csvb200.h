@@ -72,7 +72,11 @@ void csvb200_ctx_destroy(csvb200_ctx* ctx);
 const char* csvb200_last_error(const csvb200_ctx* ctx);
 /* Run all work of this context on an externally owned cudaStream_t (e.g. the caller's current
  * stream, so the caller's CUDA events bracket the kernels).  NULL restores the private stream;
- * pass cudaStreamLegacy ((cudaStream_t)0x1) to run on the legacy default stream. */
+ * pass cudaStreamLegacy ((cudaStream_t)0x1) to run on the legacy default stream.
+ * The private stream is NON-BLOCKING: it is not ordered against the legacy default stream or any
+ * other stream of the caller.  Device buffers handed to a *_device entry point must be complete
+ * (and output buffers free of pending writes) before the call: synchronise the producing stream,
+ * or make it this context's stream with this function. */
 int csvb200_ctx_set_stream(csvb200_ctx* ctx, void* cuda_stream);
 /* Initial index capacity = n / ratio_den * ratio_num + 4096 entries (default 1/3); an index that
  * overflows it is transparently rebuilt with the exact size. */

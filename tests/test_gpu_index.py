@@ -299,6 +299,7 @@ def test_full_size_properties(ctx, kind):
         sh = d[lo16:hi]
         if lo16 != lo:                       # re-materialise the shard at an aligned address
             sh = d[lo:hi].clone()
+            torch.cuda.synchronize()
         p = ctx.shard_quote_parity(sh.data_ptr(), hi - lo)
         si = ctx.index_build_shard_device(sh.data_ptr(), hi - lo, par, lo, emit_sentinel=(k == 0))
         hs = si.to_host()
@@ -389,6 +390,7 @@ def test_stream_ordered_shard_api_on_torch_stream(ctx):
                 for k in range(G):
                     ctx.shard_quote_parity_device(shards[k].data_ptr(), shards[k].numel(), pars[k:].data_ptr())
                 res = torch.zeros((G, 2), dtype=torch.int64, device=dev)
+                torch.cuda.synchronize()
                 idxs = [ctx.index_build_shard_device_ex(shards[k].data_ptr(), shards[k].numel(), pars.data_ptr(), k,
                                                         cuts[k], k == 0, res[k].data_ptr()) for k in range(G)]
                 got = np.concatenate([i.to_host() for i in idxs])
@@ -410,9 +412,10 @@ def _speculative_chain(c, raw, cuts, dev, window=0):
     G = len(cuts) - 1
     shards = [torch.from_numpy(np.frombuffer(raw, dtype=np.uint8)[cuts[k]:cuts[k + 1]].copy()).to(dev) for k in range(G)]
     res = torch.full((G, 4), 99, dtype=torch.int64, device=dev)   # garbage: the build must overwrite it
+    final = torch.zeros((G, 2), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()   # torch's stream is not ordered against the context's non-blocking stream
     idxs = [c.index_build_shard_speculative(shards[k].data_ptr(), shards[k].numel(), k, cuts[k], k == 0,
                                             res[k].data_ptr(), window) for k in range(G)]
-    final = torch.zeros((G, 2), dtype=torch.int64, device=dev)
     for i in idxs:
         i.shard_verify(res.data_ptr(), G, final.data_ptr())
     got = np.concatenate([i.to_host() for i in idxs])
@@ -621,6 +624,7 @@ def test_materialize_column_crlf_and_device_form(ctx):
         assert (offs == w_offs).all() and out.tobytes() == w_out
         d_off = torch.zeros(rc, dtype=torch.int64, device=dev)
         d_out = torch.zeros(max(len(w_out), 1), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
         idx.materialize_column_device(fld, 0, rc - 1, 3, d_off.data_ptr(), d_out.data_ptr(), len(w_out))
         torch.cuda.synchronize()
         assert (d_off.cpu().numpy().view(np.uint64) == w_offs).all()
@@ -805,6 +809,7 @@ def test_shard_build_to_host_pipeline(ctx):
     cuts = [0, cut1, (2 * n) // 3 + 7, n]
     G = 3
     res = torch.zeros((G, 4), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
     outs, jobs, lens = [], [], []
     for k in range(G):
         shard = torch.from_numpy(raw[cuts[k]:cuts[k + 1]].copy()).pin_memory()
@@ -815,6 +820,7 @@ def test_shard_build_to_host_pipeline(ctx):
         jobs.append(job)
         lens.append(ln)
     final = torch.zeros((G, 2), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
     got, redone = [], []
     for k in range(G):
         ln, rd = ctx.shard_job_verify(jobs[k], res.data_ptr(), G, final.data_ptr())
@@ -830,6 +836,7 @@ def test_shard_build_to_host_pipeline(ctx):
     want2 = O.closed_form_numpy(raw2)
     cuts2 = [0, 14 * (3 << 20) + 3, raw2.size]
     res = torch.zeros((2, 4), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
     outs, jobs = [], []
     for k in range(2):
         shard = torch.from_numpy(raw2[cuts2[k]:cuts2[k + 1]].copy()).pin_memory()
@@ -939,6 +946,7 @@ def test_more_than_2_pow_32_entries(ctx):
         pytest.skip("needs ~45 GB of free device memory")
     d = torch.full((n + 64,), 0x2C, dtype=torch.uint8, device=dev)
     d[n - 1] = 0x0A
+    torch.cuda.synchronize()
     ctx.set_reserve(1, 1)                      # one entry per byte is the worst case: no overflow rebuild
     try:
         idx = ctx.index_build_device(d.data_ptr(), n)
@@ -1001,6 +1009,7 @@ def test_gather_fields_on_a_shard_with_global_offset(ctx):
     d = torch.zeros(shard.size + 64 + 16, dtype=torch.uint8, device=dev)
     off = (-d.data_ptr()) % 16
     d[off:off + shard.size].copy_(torch.from_numpy(shard.copy()))
+    torch.cuda.synchronize()
     # emit_sentinel so that the shard's own index starts with a sentinel entry; positions are GLOBAL (>= cut)
     idx = ctx.index_build_shard_device(d.data_ptr() + off, shard.size, 0, cut, True)
     host = idx.to_host()
