@@ -1717,7 +1717,12 @@ static int materialize_multi_enqueue(csvb200_index* idx, const uint32_t* fields,
     p.nrec = nrec;
     p.flags = flags;
     p.ncols = ncols;
-    p.tiles = (nrec + 255) / 256;
+    bool distinct = true;   // the sweep unquotes in place in shared memory: a column listed twice takes the per-row kernels
+    for (uint32_t c = 0; c < ncols && distinct; ++c)
+        for (uint32_t k = 0; k < c; ++k)
+            if (fields[k] == fields[c]) distinct = false;
+    p.rows_per_tile = distinct ? materialize_sweep_plan(idx->n, idx->record_cnt, p.row_size, ncols, &p.cap_bytes) : 0u;
+    p.tiles = p.rows_per_tile ? (nrec + p.rows_per_tile - 1) / p.rows_per_tile : (nrec + 255) / 256;
     for (uint32_t c = 0; c < ncols; ++c) {
         p.field_idx[c] = fields[c];
         p.offsets[c] = d_offsets[c];
@@ -1725,7 +1730,7 @@ static int materialize_multi_enqueue(csvb200_index* idx, const uint32_t* fields,
         p.out_cap[c] = out_caps ? out_caps[c] : 0;
     }
     if (offsets_pass) {
-        const size_t sbytes = materialize_multi_scratch_bytes(nrec, ncols);
+        const size_t sbytes = materialize_multi_scratch_bytes(nrec, ncols, p.rows_per_tile);
         int rc = ensure_scratch(ctx, sbytes);
         if (rc) return rc;
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sbytes, ctx->stream));
@@ -1733,8 +1738,17 @@ static int materialize_multi_enqueue(csvb200_index* idx, const uint32_t* fields,
         p.tile_desc = reinterpret_cast<uint64_t*>(ctx->d_scratch + 128);
         if (nrec == 0)
             for (uint32_t c = 0; c < ncols; ++c) CU_TRY(ctx, cudaMemsetAsync(d_offsets[c], 0, sizeof(uint64_t), ctx->stream));
-        CU_TRY(ctx, launch_materialize_multi_offsets(p, ctx->stream));
-        if (nrec) ctx->launches += 1;
+        if (!p.rows_per_tile) {
+            CU_TRY(ctx, launch_materialize_multi_offsets(p, ctx->stream));
+            if (nrec) ctx->launches += 1;
+        }
+    }
+    if (p.rows_per_tile) {   // row sweep: offsets and values in ONE pass when both are asked for
+        if (nrec) {
+            CU_TRY(ctx, launch_materialize_sweep(p, offsets_pass, write_pass, ctx->stream));
+            if (offsets_pass || write_pass) ctx->launches += 1;
+        }
+        return CSVB200_OK;
     }
     if (write_pass && nrec) {
         CU_TRY(ctx, launch_materialize_multi_write(p, ctx->stream));

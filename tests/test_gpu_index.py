@@ -588,6 +588,68 @@ def test_tape_chunks_vs_oracle(ctx):
         idx.free()
 
 
+@pytest.mark.parametrize("sweep", ["0", "1", "32:1024", "64"])
+@pytest.mark.parametrize("flags", [0, 1, 2, 3])
+def test_materialize_columns_row_sweep_and_per_row_paths(ctx, flags, sweep, monkeypatch):
+    """Both forms of csvb200_materialize_columns on the same requests: the row sweep (tiles of R records staged through
+    shared memory; forced here, also with 32- and 64-row tiles and a 1 KiB staging area) and the per-row kernels, against the oracle.  Cases: every escape
+    shape of _column_cases, a 40 KB quoted field (its tile does not fit the staging area: per-value path inside the
+    sweep), a column listed twice (per-row kernels: the sweep unquotes in place), CRLF rows, a sub-range, clipping by out_cap in the device form."""
+    import torch
+    monkeypatch.setenv("CSVB200_MAT_SWEEP", sweep.split(":")[0])
+    if ":" in sweep:
+        monkeypatch.setenv("CSVB200_MAT_CAP", sweep.split(":")[1])   # 1 KiB staged per tile: many tiles take the per-value path
+    big = b'"' + b'ab""cd, \n' * 4000 + b'"'
+    head, rest = _column_cases().split(b"\n", 1)
+    raw = head + b"\n" + b"77, " + big + b" ,tail\n" + b"78,x,y\n" * 40 + rest
+    idx = ctx.index_build(raw, cs.BUILD_KEEP_BYTES)
+    rc, jump = idx.tape_init(3, False)
+    host = idx.to_host()
+    for fields, first, nrec in (([0, 1, 2], 0, rc - 1), ([2, 0], 17, 1000), ([1, 1, 1, 1], 0, 60), ([1, 7, 2, 2], rc - 5, 20),
+                                ([0, 1], 5, 0), ([2, 1, 0] * 5 + [1, 2], 1024, 1100)):
+        got = idx.materialize_columns(fields, first, nrec, flags)
+        for f, (offs, out) in zip(fields, got):
+            w_offs, w_out = O.materialize_column(raw, host, rc, 3, False, f, first, nrec, flags)
+            assert (offs == w_offs).all(), (fields, f, first, nrec)
+            assert out.tobytes() == w_out, (fields, f, first, nrec)
+    # device form, destination too small for the last values: whole values are clipped, nothing past out_cap is written
+    dev = torch.device("cuda", ctx.device)
+    fields, nrec = [1, 2], rc - 1
+    want = [O.materialize_column(raw, host, rc, 3, False, f, 0, nrec, flags) for f in fields]
+    caps = [len(w[1]) // 2 + 3 for w in want]
+    d_off = [torch.zeros(nrec + 1, dtype=torch.int64, device=dev) for _ in fields]
+    d_out = [torch.full((len(w[1]) + 64,), 0xEE, dtype=torch.uint8, device=dev) for w in want]
+    torch.cuda.synchronize()
+    idx.materialize_columns_device(fields, 0, nrec, flags, [t.data_ptr() for t in d_off], [t.data_ptr() for t in d_out], caps)
+    idx.sync()
+    torch.cuda.synchronize()
+    for (w_offs, w_out), cap, o, v in zip(want, caps, d_off, d_out):
+        assert (o.cpu().numpy().view(np.uint64) == w_offs).all()
+        keep = int(w_offs[w_offs <= cap].max())
+        got = v.cpu().numpy()
+        assert got[:keep].tobytes() == w_out[:keep]
+        assert (got[keep:] == 0xEE).all()
+    idx.free()
+    # CRLF rows (row_size = field_cnt + 1) and a wide quoted file against the single-column kernels
+    raw = golden_bytes("sample_rx.csv")
+    idx = ctx.index_build(raw, cs.BUILD_KEEP_BYTES)
+    rc, jump = idx.tape_init(8, True)
+    host = idx.to_host()
+    got = idx.materialize_columns([7, 0, 3, 2], 0, rc - 1, flags)
+    for f, (offs, out) in zip([7, 0, 3, 2], got):
+        w_offs, w_out = O.materialize_column(raw, host, rc, 8, True, f, 0, rc - 1, flags)
+        assert (offs == w_offs).all() and out.tobytes() == w_out
+    idx.free()
+    q, _ = gen.quoted(3 << 20, seed=43)
+    idx = ctx.index_build(q, cs.BUILD_KEEP_BYTES)
+    rc, _ = idx.tape_init(16, True)
+    got = idx.materialize_columns(list(range(16)), 0, rc - 1, flags)
+    for f in (0, 1, 7, 15):
+        offs, out = idx.materialize_column(f, 0, rc - 1, flags)
+        assert (got[f][0] == offs).all() and got[f][1].tobytes() == out.tobytes()
+    idx.free()
+
+
 def _column_cases():
     rows = [b'id,name,note']
     vals = [b'plain', b'"quoted"', b'  padded\t', b'"with ""escapes"" inside"', b'""', b'"', b'', b' "q, and\nnewline" ',
