@@ -152,25 +152,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             : "memory");
     } while (!ok);
 }
-// The same for the two service warps (producer, look-back), which wait for most of a super-tile period: ptxas turns
-// try_wait into a SYNCS.TRYWAIT + NANOSLEEP.SYNCS loop that comes back every ~12 ns (ncu, round 2: 50 M of the kernel's
-// 300 M warp instructions were these three), so a failed try sleeps `ns` before the next one.
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns)
-{
-    const uint32_t addr = smem_u32(bar);
-    for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(2000u)
-            : "memory");
-        if (ok) break;
-        if (ns) __nanosleep(ns);
-    }
-}
+// (ptxas turns try_wait into a SYNCS.TRYWAIT + NANOSLEEP.SYNCS loop that comes back every ~12 ns: the two service warps,
+// which wait for most of a super-tile period, execute 50 M of the kernel's 300 M warp instructions that way (ncu, round
+// 2).  Sleeping 64 / 128 / 256 ns after a failed try -- look-back warp alone or the producer too -- changed nothing:
+// 0.3765 / 0.3410 ms against 0.3758-0.3764 / 0.3405-0.3420, profiles/r02_kvariants.md kv13: the spinning warps only take
+// issue slots nobody else wants.)
 __device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap* tmap, int32_t c0, int32_t c1, uint64_t* bar)
 {
     asm volatile(
@@ -321,9 +307,6 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
     constexpr int kSub = S::kSub, kSkew = S::kSkew, kRing = S::kRing, kWorkerWarps = S::kWorkers;
-    // A/B (CSVB200_TUNE bits 32, 64: back-off of the look-back warp's waits 64 / 128 / 256 ns; bit 128: the producer's too)
-    const uint32_t lb_ns = ((p.tune >> 5) & 3u) == 0u ? 0u : 32u << ((p.tune >> 5) & 3u);
-    const uint32_t pr_ns = (p.tune & 128u) ? lb_ns : 0u;
     const bool jit = (p.tune & 4u) == 0u;   // CSVB200_TUNE bit 4: draw tickets as soon as a ring slot frees (round 1; A/B)
     const uint32_t go_at = !jit ? 0u : ((p.tune >> 3) & 3u) == 1u ? 1u : ((p.tune >> 3) & 3u) == 2u ? 3u : 2u;   // A/B: bits 8, 16
 
@@ -355,7 +338,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 // as a ring slot frees.  A ticket held for a whole period before its tile is classified makes every
                 // later tile wait for an aggregate that is a period away -- and a CTA that waits for its prefix holds
                 // such a ticket the whole time it waits.
-                if (jit && it > 0u) mbar_wait_backoff(&sm.go, (it - 1u) & 1u, pr_ns);
+                if (jit && it > 0u) mbar_wait(&sm.go, (it - 1u) & 1u);
                 // dynamic super-tile id: a tile only ever waits on tiles whose CTAs already hold a ticket.
                 // (Taking the NEXT ticket early to hide the atomic's round trip measured slower, 0.423 vs
                 // 0.418 ms: a ticket held for a whole super-tile period before its loads start delays the
@@ -368,7 +351,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
 #pragma unroll
                 for (int sub = 0; sub < kSub; ++sub) {
                     const uint32_t sc = it * kSub + sub, st = sc % S::kSlots;
-                    mbar_wait_backoff(&sm.empty[st], ((sc / S::kSlots) & 1u) ^ 1u, pr_ns);
+                    mbar_wait(&sm.empty[st], ((sc / S::kSlots) & 1u) ^ 1u);
                     sm.tile_id[st] = tile;
                     if (tile == kInvalidTile) {
                         mbar_arrive(&sm.full[st]);
@@ -390,7 +373,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
         uint32_t cta_hi = 0u;        // (validate) a byte >= 0x80 was seen
         for (uint32_t it = 0;; ++it) {
             const uint32_t b = it % kRing;
-            mbar_wait_backoff(&sm.agg_full[b], (it / kRing) & 1u, lb_ns);
+            mbar_wait(&sm.agg_full[b], (it / kRing) & 1u);
             const uint32_t tile = sm.agg_tile[b];
             if (tile == kInvalidTile) break;
             PrefixInfo<kSub, kWorkerWarps>& pi = sm.pref[b];

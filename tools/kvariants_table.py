@@ -26,8 +26,10 @@ def label(run: int, t: int) -> str:
             nm += ", go right after the prefix wait"
         if (m & 24) == 16:
             nm += ", go after the whole compaction"
-        if m & 32:
+        if run == 12 and (m & 32):
             nm += ", copy-out with one 32-bit add per entry"
+        if run == 13 and (m & 0xE0):
+            nm += f", service-warp waits back off {32 << ((m >> 5) & 3)} ns after a failed try ({'look-back and producer' if m & 128 else 'look-back warp'})"
     if m & 0x400:
         nm += " + NO CHAIN (timing experiment: every look-back answered on its first poll)"
     return nm
