@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +33,14 @@ SlicePool& io_pool(csvb200_ctx* ctx)
 {
     if (!ctx->pool) ctx->pool = new SlicePool(default_io_threads());
     return *ctx->pool;
+}
+
+// The pageable end-to-end pipeline copies into staging (uploads) and out of the bounce buffers (downloads) at the
+// same time, from two host threads: each side has its own slices (SlicePool::run is one job at a time).
+SlicePool& io_pool_down(csvb200_ctx* ctx)
+{
+    if (!ctx->pool_down) ctx->pool_down = new SlicePool(default_io_threads());
+    return *ctx->pool_down;
 }
 
 bool is_pinned(const void* p)
@@ -367,7 +377,7 @@ int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n)
     while (off < n) {
         const size_t len = std::min(kStageBytes, n - off);
         CU_TRY(ctx, cudaEventSynchronize(ctx->stage_free[b]));
-        parallel_memcpy(io_pool(ctx), ctx->h_stage[b], h_src + off, len);   // one thread cannot feed PCIe
+        parallel_memcpy(io_pool(ctx), ctx->h_stage[b], h_src + off, len, CopyDir::ToStaging);   // one thread cannot feed PCIe
         CU_TRY(ctx, cudaMemcpyAsync(d_dst + off, ctx->h_stage[b], len, cudaMemcpyHostToDevice, ctx->stream));
         CU_TRY(ctx, cudaEventRecord(ctx->stage_free[b], ctx->stream));
         off += len;
@@ -508,6 +518,7 @@ void csvb200_ctx_destroy(csvb200_ctx* ctx)
     if (ctx->d_cells) cudaFree(ctx->d_cells);
     if (ctx->h_cells) cudaFreeHost(ctx->h_cells);
     delete ctx->pool;
+    delete ctx->pool_down;
     for (int i = 0; i < 2; ++i) {
         if (ctx->h_bounce[i]) cudaFreeHost(ctx->h_bounce[i]);
         if (ctx->bounce_done[i]) cudaEventDestroy(ctx->bounce_done[i]);
@@ -821,8 +832,18 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
             cudaFreeAsync(d_bytes, s_up);
         cudaFreeAsync(d_index, s_up);
     };
-    // ---- enqueue every upload + launch; nothing here waits on the host ----
-    for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
+    // ---- enqueue every upload + launch ----
+    // Pinned (or device-resident) input: nothing here waits on the host, the whole schedule is enqueued before the first
+    // download is looked at.  Pageable input: every upload is a host copy into pinned staging, so this side runs on its
+    // own thread and the calling thread starts the downloads as the chunks finish -- the two host copies (input into
+    // staging, index out of the bounce buffers) and the two DMA directions all overlap.
+    std::atomic<size_t> enqueued{0};       // chunks whose `done` event is recorded
+    std::atomic<bool> enqueue_failed{false};
+    int rc_up = CSVB200_OK;
+    auto enqueue_all = [&]() {
+      int& rc = rc_up;
+      if (cudaSetDevice(ctx->device) != cudaSuccess) rc = CSVB200_ERR_CUDA;
+      for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
         const size_t off = chunk_off[c], len = chunk_off[c + 1] - off;
         if (!o.d_bytes_in) rc = upload(ctx, d_bytes + off, host_bytes + off, len);
         if (rc) break;
@@ -867,16 +888,27 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
             cudaGetLastError();
             rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
         }
-    }
-    if (rc == CSVB200_OK && o.d_result4) {
-        // {entries, end parity} of the last chunk, the carry parity the first chunk used; the separator total was
-        // accumulated by the launches themselves
-        cudaError_t e = cudaMemcpyAsync(o.d_result4, d_cells + nchunks * kCellWords, 2 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s_up);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(o.d_result4 + 2, d_cells + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s_up);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
-        }
+        if (rc == CSVB200_OK) enqueued.store(c + 1, std::memory_order_release);
+      }
+      if (rc == CSVB200_OK && o.d_result4) {
+          // {entries, end parity} of the last chunk, the carry parity the first chunk used; the separator total was
+          // accumulated by the launches themselves
+          cudaError_t e = cudaMemcpyAsync(o.d_result4, d_cells + nchunks * kCellWords, 2 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s_up);
+          if (e == cudaSuccess) e = cudaMemcpyAsync(o.d_result4 + 2, d_cells + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s_up);
+          if (e != cudaSuccess) {
+              cudaGetLastError();
+              rc = fail(ctx, CSVB200_ERR_CUDA, std::string("e2e pipeline: ") + cudaGetErrorString(e));
+          }
+      }
+      if (rc != CSVB200_OK) enqueue_failed.store(true, std::memory_order_release);
+    };
+    const bool two_threads = !o.d_bytes_in && n >= (64u << 20) && !is_pinned(host_bytes);
+    std::thread uploader;
+    if (two_threads) {
+        uploader = std::thread(enqueue_all);
+    } else {
+        enqueue_all();
+        rc = rc_up;
     }
     // ---- as each chunk's kernel finishes, send its index segment down on the second stream ----
     // A pinned destination is DMA'd in place.  A pageable one (a plain Vec<usize>) would make every copy a
@@ -888,12 +920,15 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
     auto flush_piece = [&](size_t k) -> cudaError_t {   // piece k (in order): wait for its D2H, copy it to dst
         const int b = (int)(k & 1);
         cudaError_t e = cudaEventSynchronize(ctx->bounce_done[b]);
-        if (e == cudaSuccess) parallel_memcpy(io_pool(ctx), dst + piece_pos[b], ctx->h_bounce[b], piece_len[b] * sizeof(uint64_t));
+        if (e == cudaSuccess) parallel_memcpy(io_pool_down(ctx), dst + piece_pos[b], ctx->h_bounce[b], piece_len[b] * sizeof(uint64_t));
         return e;
     };
     size_t copied = 0;  // entries already on their way to dst (including the sentinel)
     bool overflow = false, dst_small = false;
     for (size_t c = 0; c < nchunks && rc == CSVB200_OK; ++c) {
+        while (enqueued.load(std::memory_order_acquire) <= c && !enqueue_failed.load(std::memory_order_acquire))
+            std::this_thread::yield();     // (pageable input) the uploader has not reached this chunk yet
+        if (enqueued.load(std::memory_order_acquire) <= c) break;   // the uploader failed: its status is reported below
         cudaError_t e = cudaEventSynchronize(done[c]);
         if (e == cudaSuccess) {
             const size_t upto = (size_t)out_base + (size_t)h_cells[(c + 1) * kCellWords];  // entries through this chunk
@@ -938,6 +973,8 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
             rc = fail(ctx, CSVB200_ERR_CUDA, "e2e pipeline: bounce copy failed");
         }
     }
+    if (uploader.joinable()) uploader.join();
+    if (rc == CSVB200_OK) rc = rc_up;
     if (rc == CSVB200_OK) {
         cudaError_t e = cudaStreamSynchronize(s_down);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s_up);

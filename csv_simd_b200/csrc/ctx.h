@@ -51,6 +51,7 @@ struct csvb200_ctx {
     uint64_t* h_bounce[2] = {nullptr, nullptr};   // pinned bounce buffers for index segments headed to pageable memory
     cudaEvent_t bounce_done[2] = {nullptr, nullptr};
     csvb200::SlicePool* pool = nullptr;   // host threads for pread / staging copies, created on first use (io_pool)
+    csvb200::SlicePool* pool_down = nullptr;   // a second set for the download side of the pageable pipeline (io_pool_down)
     uint8_t* h_seek_stage = nullptr;   // pinned staging of the batched seeks from pageable arrays (kept across calls)
     size_t seek_stage_bytes = 0;
     uint8_t* h_stage[csvb200::kStageBufs] = {nullptr, nullptr};

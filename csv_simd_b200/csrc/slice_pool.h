@@ -9,6 +9,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace csvb200 {
 
@@ -77,8 +80,64 @@ private:
     bool stop_ = false;
 };
 
-inline void parallel_memcpy(SlicePool& pool, void* dst, const void* src, size_t bytes)
+// memcpy with non-temporal stores: the staging copies of the end-to-end path move gigabytes that nobody reads back from
+// cache (the DMA engine or the caller, much later), and they are bound by host memory traffic -- a plain store first
+// reads the destination line (read-for-ownership), i.e. 3 units of traffic per byte copied instead of 2.  glibc switches
+// to streaming stores only above a per-call threshold that the 2-4 MiB slices here stay under.
+inline void stream_memcpy(void* dst, const void* src, size_t bytes)
 {
+#if defined(__SSE2__)
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    const uint8_t* s = static_cast<const uint8_t*>(src);
+    if (bytes < 4096) {
+        std::memcpy(d, s, bytes);
+        return;
+    }
+    const size_t head = (size_t)(-(uintptr_t)d & 63u);
+    std::memcpy(d, s, head);
+    d += head;
+    s += head;
+    bytes -= head;
+    const size_t body = bytes & ~size_t(63);
+    for (size_t i = 0; i < body; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32));
+        const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
+    }
+    _mm_sfence();
+    std::memcpy(d + body, s + body, bytes - body);
+#else
+    std::memcpy(dst, src, bytes);
+#endif
+}
+
+// CSVB200_STREAM_COPY (A/B): bit 0 = copies INTO pinned staging stream, bit 1 = copies out of the bounce buffers into
+// the caller's array stream; default 3.  Measured on two 16-vCPU B200 hosts, 1 GiB of cfg2, ms per call
+// (tools/pageable_probe.py; pinned both sides: 25.6 / 26.9):
+//                               mask 0         1         3
+//   pageable in,  pinned out    37.5 / 38.8    35.8      32.2 / 35.8
+//   pinned in,  pageable out    34.2 / 43.5    44.8      39.4 / 43.4
+//   pageable both               51.1 / 60.4    55.9      41.4 / 52.0
+// (the caller the path is for -- an mmap in, a Vec<usize> out -- is the last row).
+inline int stream_copy_mask()
+{
+    static const int mask = [] {
+        const char* e = std::getenv("CSVB200_STREAM_COPY");
+        return e ? std::atoi(e) : 3;
+    }();
+    return mask;
+}
+
+enum class CopyDir { ToStaging, ToCaller };
+
+inline void parallel_memcpy(SlicePool& pool, void* dst, const void* src, size_t bytes, CopyDir dir = CopyDir::ToCaller)
+{
+    const bool nt = (stream_copy_mask() & (dir == CopyDir::ToStaging ? 1 : 2)) != 0;
     if (bytes < (4u << 20)) {
         std::memcpy(dst, src, bytes);
         return;
@@ -86,7 +145,11 @@ inline void parallel_memcpy(SlicePool& pool, void* dst, const void* src, size_t 
     pool.run([&](int i, int n) {
         const size_t per = ((bytes + n - 1) / n + 63) & ~size_t(63);
         const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
-        if (b > a) std::memcpy(static_cast<uint8_t*>(dst) + a, static_cast<const uint8_t*>(src) + a, b - a);
+        if (b <= a) return;
+        if (nt)
+            stream_memcpy(static_cast<uint8_t*>(dst) + a, static_cast<const uint8_t*>(src) + a, b - a);
+        else
+            std::memcpy(static_cast<uint8_t*>(dst) + a, static_cast<const uint8_t*>(src) + a, b - a);
     });
 }
 
