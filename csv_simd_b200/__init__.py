@@ -5,7 +5,7 @@ Compute lives in csrc/ (hand-written CUDA behind the C ABI in include/csvb200.h)
 the ctypes binding plus the host-side mirror of the reference's public API.  No CPU fallback.
 """
 from .api import (BUILD_DEFAULT, BUILD_KEEP_BYTES, BUILD_STRICT_MIN64, BUILD_VALIDATE, FIELD_RAW, FIELD_TRIM,  # noqa: F401
-                  FIELD_UNQUOTE, Context, Exchange, Multi, StructureIndex)
+                  FIELD_UNQUOTE, Context, Exchange, Multi, StructureIndex, host_registered)
 from . import errors  # noqa: F401
 from .errors import (GpuError, InvalidCsvFormat, InvalidState, Io, MissingValue, ReferencePanic,  # noqa: F401
                      StructureError)
@@ -17,5 +17,5 @@ __all__ = [
     "NewLine", "Boundary", "Chunk", "boundaries", "StructureError", "Io", "MissingValue", "InvalidState",
     "InvalidCsvFormat", "ReferencePanic", "GpuError", "BUILD_DEFAULT", "BUILD_KEEP_BYTES", "BUILD_STRICT_MIN64", "BUILD_VALIDATE",
     "FIELD_RAW", "FIELD_UNQUOTE", "FIELD_TRIM",
-    "default_context",
+    "default_context", "host_registered",
 ]

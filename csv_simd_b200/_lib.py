@@ -66,6 +66,8 @@ SIGNATURES = {
     "csvb200_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "csvb200_host_alloc": (C.c_int, [C.c_size_t, vpp]),
     "csvb200_host_free": (C.c_int, [C.c_void_p]),
+    "csvb200_host_register": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int]),
+    "csvb200_host_unregister": (C.c_int, [C.c_void_p]),
     "csvb200_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, vpp]),
     "csvb200_index_build_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, vpp]),
     "csvb200_index_build_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, szp]),

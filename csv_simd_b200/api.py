@@ -22,6 +22,25 @@ FIELD_TRIM = 2
 NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
+class host_registered:
+    """Pins a NumPy array the caller owns for the duration of a `with` block (csvb200_host_register / _unregister), so the
+    end-to-end calls DMA it in place: `with host_registered(out): ctx.index_build_to_host(...)`."""
+
+    def __init__(self, array: np.ndarray, read_only: bool = False):
+        self._ptr, self._bytes, self._ro = array.ctypes.data, array.nbytes, read_only
+        self._array = array           # keeps the memory alive while it is registered
+
+    def __enter__(self):
+        rc = _lib.load().csvb200_host_register(C.c_void_p(self._ptr), self._bytes, int(self._ro))
+        if rc:
+            raise_for(rc, "csvb200_host_register")
+        return self._array
+
+    def __exit__(self, *exc):
+        _lib.load().csvb200_host_unregister(C.c_void_p(self._ptr))
+        return False
+
+
 def _as_u8(data) -> np.ndarray:
     if isinstance(data, np.ndarray):
         a = data

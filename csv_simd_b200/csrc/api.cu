@@ -587,6 +587,31 @@ int csvb200_host_free(void* p)
     return cudaFreeHost(p) == cudaSuccess ? CSVB200_OK : CSVB200_ERR_CUDA;
 }
 
+int csvb200_host_register(void* p, size_t bytes, int read_only)
+{
+    if (!p || bytes == 0) return CSVB200_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostRegister(p, bytes, read_only ? cudaHostRegisterReadOnly : cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (e == cudaErrorMemoryAllocation) return CSVB200_ERR_OOM;
+        return (e == cudaErrorHostMemoryAlreadyRegistered || e == cudaErrorInvalidValue || e == cudaErrorNotSupported)
+                   ? CSVB200_ERR_INVALID_ARG
+                   : CSVB200_ERR_CUDA;
+    }
+    return CSVB200_OK;
+}
+
+int csvb200_host_unregister(void* p)
+{
+    if (!p) return CSVB200_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorHostMemoryNotRegistered || e == cudaErrorInvalidValue ? CSVB200_ERR_INVALID_ARG : CSVB200_ERR_CUDA;
+    }
+    return CSVB200_OK;
+}
+
 int csvb200_index_build_device(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint32_t flags, csvb200_index** out)
 {
     if (ctx && (flags & CSVB200_BUILD_STRICT_MIN64) && n < 64)

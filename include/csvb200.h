@@ -89,6 +89,12 @@ uint64_t csvb200_ctx_launch_count(const csvb200_ctx* ctx);
 /* pinned host memory for staging (cudaHostAlloc / cudaFreeHost) */
 int csvb200_host_alloc(size_t bytes, void** out);
 int csvb200_host_free(void* p);
+/* Pin memory the caller already owns (a Vec<usize> it reuses, an Mmap) so that the end-to-end calls DMA it in
+ * place instead of staging it through host copies (cudaHostRegister; read_only != 0 for a PROT_READ mapping).
+ * Costs ~25-30 ms per GiB, so it pays for buffers used more than once.  The range must stay mapped until
+ * csvb200_host_unregister(p) (same pointer).  CSVB200_ERR_INVALID_ARG: already registered / not registrable. */
+int csvb200_host_register(void* p, size_t bytes, int read_only);
+int csvb200_host_unregister(void* p);
 
 /* ---- csv -> index : replaces reader::read (src/reader.rs:150-306) -------------------------- */
 /* Host bytes -> device-resident index.  Copies the input to the GPU in chunks

@@ -650,6 +650,23 @@ def test_materialize_columns_row_sweep_and_per_row_paths(ctx, flags, sweep, monk
     idx.free()
 
 
+def test_host_register_pins_caller_memory(ctx):
+    """csvb200_host_register: an ordinary array becomes DMA-able in place (the end-to-end call takes its pinned branch),
+    the result equals the oracle's, a second registration of the same range is refused, unregister restores it."""
+    q, _ = gen.quoted(96 << 20, seed=51)
+    want = O.read_sse(q)
+    out = np.zeros(want.size + 64, dtype=np.uint64)
+    lib = cs._lib.load()
+    with cs.host_registered(out), cs.host_registered(q, read_only=False):
+        assert lib.csvb200_host_register(out.ctypes.data, out.nbytes, 0) == 1      # CSVB200_ERR_INVALID_ARG
+        ln = ctx.index_build_to_host(q.ctypes.data, q.size, out.ctypes.data, out.size)
+        assert ln == want.size and (out[:ln] == want).all()
+    assert lib.csvb200_host_unregister(out.ctypes.data) == 1                        # no longer registered
+    out[:] = 0
+    ln = ctx.index_build_to_host(q.ctypes.data, q.size, out.ctypes.data, out.size)   # pageable again: staged copies
+    assert ln == want.size and (out[:ln] == want).all()
+
+
 def _column_cases():
     rows = [b'id,name,note']
     vals = [b'plain', b'"quoted"', b'  padded\t', b'"with ""escapes"" inside"', b'""', b'"', b'', b' "q, and\nnewline" ',
