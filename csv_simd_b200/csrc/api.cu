@@ -87,7 +87,7 @@ int ensure_scratch(csvb200_ctx* ctx, size_t bytes)
     if (ctx->d_scratch) CU_TRY(ctx, cudaFreeAsync(ctx->d_scratch, ctx->stream));
     ctx->d_scratch = nullptr;
     ctx->scratch_bytes = 0;
-    CU_TRY(ctx, cudaMallocAsync((void**)&ctx->d_scratch, nb, ctx->stream));
+    CU_TRY(ctx, pool_malloc((void**)&ctx->d_scratch, nb, ctx->stream));
     ctx->scratch_bytes = nb;
     return CSVB200_OK;
 }
@@ -100,7 +100,7 @@ int next_build_scratch(csvb200_ctx* ctx, size_t bytes, cudaStream_t stream, uint
         if (ctx->d_bscratch) CU_TRY(ctx, cudaFreeAsync(ctx->d_bscratch, stream));
         ctx->d_bscratch = nullptr;
         ctx->bscratch_bytes = 0;
-        CU_TRY(ctx, cudaMallocAsync((void**)&ctx->d_bscratch, nb, stream));
+        CU_TRY(ctx, pool_malloc((void**)&ctx->d_bscratch, nb, stream));
         ctx->bscratch_bytes = nb;
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_bscratch, 0, nb, stream));
         ctx->desc_tag = 0;
@@ -212,7 +212,7 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             // by-products: newline count and non-ASCII flag accumulate in the zeroed head of the scratch, the per-tile
             // non-ASCII bitmap belongs to the index (K7 later visits the flagged tiles only)
             const size_t words = (size_t)(num_tiles + 31) / 32;
-            if (!idx->d_nonascii) CU_TRY(ctx, cudaMallocAsync((void**)&idx->d_nonascii, words * sizeof(uint32_t), ctx->stream));
+            if (!idx->d_nonascii) CU_TRY(ctx, pool_malloc((void**)&idx->d_nonascii, words * sizeof(uint32_t), ctx->stream));
             CU_TRY(ctx, cudaMemsetAsync(idx->d_nonascii, 0, words * sizeof(uint32_t), ctx->stream));
             idx->flag_tile_bytes = build_flag_tile_bytes(n, use_tma, ctx->tune);
             p.validate = 1u;
@@ -333,11 +333,17 @@ int build_device_common(csvb200_ctx* ctx, const void* dev_bytes, size_t n, uint3
         idx->predict_window = predict_window ? predict_window : kDefaultPredictWindow;
     }
     idx->cap = initial_cap(ctx, n);
-    cudaError_t e = cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream);
+    const size_t idx_bytes = idx->cap * sizeof(uint64_t);
+    cudaError_t e = pool_malloc((void**)&idx->d_index, idx_bytes, ctx->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         csvb200_index_free(idx);
-        return fail(ctx, CSVB200_ERR_OOM, std::string("index allocation: ") + cudaGetErrorString(e));
+        size_t mem_free = 0, mem_total = 0;
+        cudaMemGetInfo(&mem_free, &mem_total);
+        cudaGetLastError();
+        return fail(ctx, CSVB200_ERR_OOM, "index allocation of " + std::to_string(idx_bytes) + " bytes on device " +
+                                              std::to_string(ctx->device) + ": " + cudaGetErrorString(e) + " (" +
+                                              std::to_string(mem_free >> 20) + " of " + std::to_string(mem_total >> 20) + " MiB free)");
     }
     rc = enqueue_build(idx, true);
     if (!rc && ex) {
@@ -836,8 +842,8 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
     uint64_t* d_index = nullptr;
     const size_t cap = initial_cap(ctx, n);
     const uint64_t out_base = o.emit_sentinel ? 1 : 0;
-    if (!d_bytes) CU_TRY(ctx, cudaMallocAsync((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, s_up));
-    CU_TRY(ctx, cudaMallocAsync((void**)&d_index, cap * sizeof(uint64_t), s_up));
+    if (!d_bytes) CU_TRY(ctx, pool_malloc((void**)&d_bytes, ((n + 15) & ~size_t(15)) + 16, s_up));
+    CU_TRY(ctx, pool_malloc((void**)&d_index, cap * sizeof(uint64_t), s_up));
     uint64_t* d_cells = ctx->d_cells + cell0 * kCellWords;
     uint64_t* h_cells = ctx->h_cells + cell0 * kCellWords;
     if (o.d_carry0)
@@ -927,7 +933,11 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
       }
       if (rc != CSVB200_OK) enqueue_failed.store(true, std::memory_order_release);
     };
-    const bool two_threads = !o.d_bytes_in && n >= (64u << 20) && !is_pinned(host_bytes);
+    static const bool upload_thread = [] {
+        const char* e = std::getenv("CSVB200_E2E_UPLOAD_THREAD");   // 0: enqueue everything first, on the calling thread (A/B)
+        return !(e && e[0] == '0');
+    }();
+    const bool two_threads = upload_thread && !o.d_bytes_in && n >= (64u << 20) && !is_pinned(host_bytes);
     std::thread uploader;
     if (two_threads) {
         uploader = std::thread(enqueue_all);
@@ -1265,7 +1275,7 @@ int csvb200_index_sync(csvb200_index* idx)
         CU_TRY(ctx, cudaFreeAsync(idx->d_index, ctx->stream));
         idx->d_index = nullptr;
         idx->cap = len + 2;
-        CU_TRY(ctx, cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream));
+        CU_TRY(ctx, pool_malloc((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream));
         int rc = enqueue_build(idx, true);
         if (rc) return rc;
     }
@@ -1514,10 +1524,10 @@ static int seek_host(csvb200_index* idx, const uint32_t* rec, const uint32_t* fl
                         std::string(#expr) + ": " + cudaGetErrorString(e_));                               \
         }                                                                                                  \
     } while (0)
-    SEEK_TRY(cudaMallocAsync((void**)&d_rec, nslots * chunk * sizeof(uint32_t), s_up));
-    if (fld) SEEK_TRY(cudaMallocAsync((void**)&d_fld, nslots * chunk * sizeof(uint32_t), s_up));
-    SEEK_TRY(cudaMallocAsync((void**)&d_out, nslots * chunk * sizeof(csvb200_range), s_up));
-    SEEK_TRY(cudaMallocAsync((void**)&d_oob, sizeof(uint32_t), s_up));
+    SEEK_TRY(pool_malloc((void**)&d_rec, nslots * chunk * sizeof(uint32_t), s_up));
+    if (fld) SEEK_TRY(pool_malloc((void**)&d_fld, nslots * chunk * sizeof(uint32_t), s_up));
+    SEEK_TRY(pool_malloc((void**)&d_out, nslots * chunk * sizeof(csvb200_range), s_up));
+    SEEK_TRY(pool_malloc((void**)&d_oob, sizeof(uint32_t), s_up));
     SEEK_TRY(cudaMemsetAsync(d_oob, 0, sizeof(uint32_t), s_up));
     if (!direct) {
         if (ctx->seek_stage_bytes < nslots * slot_bytes) {   // page-locking is slow: keep the buffer in the context
@@ -2000,7 +2010,7 @@ int csvb200_index_load(csvb200_ctx* ctx, const char* path, csvb200_index** out)
     int rc = new_index(ctx, &idx);
     if (rc) return rc;
     idx->cap = host.size();
-    cudaError_t e = cudaMallocAsync((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream);
+    cudaError_t e = pool_malloc((void**)&idx->d_index, idx->cap * sizeof(uint64_t), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx->d_index, host.data(), host.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {

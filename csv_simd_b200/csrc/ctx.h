@@ -158,6 +158,27 @@ SlicePool& io_pool(csvb200_ctx* ctx);   // the context's host-thread pool (CSVB2
 // pageable ones through the context's pinned staging ring
 int upload(csvb200_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n);
 
+// cudaMallocAsync from the device's default pool.  The pool keeps every freed block (release threshold = max, set at
+// context creation) and, once csvb200_multi_create has granted peer devices access to it, can answer a small request
+// with "out of memory" while the device is all but empty (seen on a 2-GPU box: 34 MB refused with 181 GB free, after
+// earlier contexts of the process had left cached blocks behind).  Handing the unused blocks back to the driver and
+// asking again resolves it, so every stream-ordered allocation of the library goes through here.
+inline cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t s)
+{
+    cudaError_t e = cudaMallocAsync(p, bytes, s);
+    if (e != cudaErrorMemoryAllocation) return e;
+    cudaGetLastError();
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess ||
+        cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return cudaErrorMemoryAllocation;
+    }
+    cudaMemPoolTrimTo(pool, 0);
+    return cudaMallocAsync(p, bytes, s);
+}
+
 // stream-ordered device allocation released on scope exit (error paths included)
 struct DevBuf {
     void* p = nullptr;
@@ -170,7 +191,7 @@ struct DevBuf {
     {
         reset();
         stream = s;
-        return cudaMallocAsync(&p, bytes ? bytes : 1, s);
+        return pool_malloc(&p, bytes ? bytes : 1, s);
     }
     void reset()
     {

@@ -259,7 +259,7 @@ void shard_phase1(csvb200_multi* m, int k, const uint8_t* bytes, size_t n, uint6
     csvb200_ctx* ctx = m->ctx[k];
     const double t0 = now_s();
     cudaError_t e = cudaSetDevice(ctx->device);
-    if (e == cudaSuccess) e = cudaMallocAsync((void**)&w->d_bytes, ((n + 15) & ~size_t(15)) + 16, ctx->stream);
+    if (e == cudaSuccess) e = pool_malloc((void**)&w->d_bytes, ((n + 15) & ~size_t(15)) + 16, ctx->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         w->rc = CSVB200_ERR_OOM;

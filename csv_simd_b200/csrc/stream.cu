@@ -103,8 +103,8 @@ struct Pipeline {
             s.h_in = ctx->h_stream_in[si];
             s.h_out = ctx->h_stream_out[si];
             ++si;
-            CU_TRY(ctx, cudaMallocAsync((void**)&s.d_in, chunk + 16, ctx->stream));
-            CU_TRY(ctx, cudaMallocAsync((void**)&s.d_seg, (chunk + 2) * sizeof(uint64_t), ctx->stream));
+            CU_TRY(ctx, pool_malloc((void**)&s.d_in, chunk + 16, ctx->stream));
+            CU_TRY(ctx, pool_malloc((void**)&s.d_seg, (chunk + 2) * sizeof(uint64_t), ctx->stream));
             CU_TRY(ctx, cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
             CU_TRY(ctx, cudaEventCreateWithFlags(&s.d_done, cudaEventDisableTiming));
         }
