@@ -31,7 +31,7 @@ int fail(csvb200_ctx* ctx, int code, const std::string& msg)
 
 SlicePool& io_pool(csvb200_ctx* ctx)
 {
-    if (!ctx->pool) ctx->pool = new SlicePool(default_io_threads());
+    if (!ctx->pool) ctx->pool = new SlicePool(ctx->io_threads > 0 ? ctx->io_threads : default_io_threads());
     return *ctx->pool;
 }
 
@@ -39,7 +39,7 @@ SlicePool& io_pool(csvb200_ctx* ctx)
 // same time, from two host threads: each side has its own slices (SlicePool::run is one job at a time).
 SlicePool& io_pool_down(csvb200_ctx* ctx)
 {
-    if (!ctx->pool_down) ctx->pool_down = new SlicePool(default_io_threads());
+    if (!ctx->pool_down) ctx->pool_down = new SlicePool(ctx->io_threads > 0 ? ctx->io_threads : default_io_threads());
     return *ctx->pool_down;
 }
 

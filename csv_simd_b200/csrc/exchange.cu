@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "slice_pool.h"
 
 using namespace csvb200;
 
@@ -302,6 +303,7 @@ int csvb200_multi_create(const int* devices, int ndev, csvb200_multi** out)
         csvb200_ctx* c = nullptr;
         rc = csvb200_ctx_create(devices[k], &c);
         if (rc) break;
+        c->io_threads = std::max(2, default_io_threads() / ndev);   // the host's copy threads are shared by all devices
         m->ctx.push_back(c);
         m->device.push_back(devices[k]);
         csvb200_exchange* ex = nullptr;
