@@ -1776,6 +1776,9 @@ static int materialize_multi_enqueue(csvb200_index* idx, const uint32_t* fields,
                                      const size_t* out_caps, bool offsets_pass, bool write_pass)
 {
     csvb200_ctx* ctx = idx->ctx;
+    if (ncols == 1 && !getenv("CSVB200_MAT_SWEEP"))   // one column: the single-column kernels (1024-record tiles) are the faster form
+        return materialize_enqueue(idx, fields[0], first_record, nrec, flags, d_offsets[0], d_outs ? d_outs[0] : nullptr,
+                                   out_caps ? out_caps[0] : 0, offsets_pass, write_pass);
     MaterializeMultiParams p{};
     p.index = idx->d_index;
     p.index_len = idx->len;

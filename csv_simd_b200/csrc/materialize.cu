@@ -40,6 +40,48 @@ __device__ __forceinline__ void st_relaxed(uint64_t* p, uint64_t v)
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Decoupled look-back by a whole warp: publishes this tile's total, sums the totals of the tiles before it back to the
+// nearest published prefix, publishes prefix + total and returns the prefix (every lane).  Tiles are small, so tiles
+// start faster than one 32-descriptor hop (~0.7 us of L2 latency) could follow: with one window per hop the nearest
+// published prefix drifts away until every look-back walks all the tiles in flight.  Four windows (128 tiles) are
+// fetched at once per hop, the loads overlapped.  Tiles must be taken in ticket order.
+__device__ __forceinline__ uint64_t lookback_warp(uint64_t* desc, uint32_t tile, uint64_t total, uint32_t lane)
+{
+    if (lane == 0) st_relaxed(desc + tile, kMatAgg | (total & kMatMask));
+    uint64_t prefix = 0;
+    for (int64_t t = (int64_t)tile - 1; t >= 0;) {
+        uint64_t d[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int64_t mine = t - 32 * w - (int64_t)lane;
+            d[w] = mine >= 0 ? ld_relaxed(desc + mine) : kMatPrefix;          // before tile 0: prefix 0
+        }
+        bool done = false, retry = false;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (done || retry) break;
+            const uint32_t st = (uint32_t)(d[w] >> 62);
+            const uint32_t pref = __ballot_sync(0xffffffffu, st == 2u), wait = __ballot_sync(0xffffffffu, st == 0u);
+            const uint32_t upto = pref ? (uint32_t)__ffs((int)pref) - 1u : 31u;  // lanes 0 .. upto count
+            const uint32_t use = 0xffffffffu >> (31u - upto);
+            if (wait & use) {
+                retry = true;                                                 // resume from this window
+                break;
+            }
+            uint64_t v = (use >> lane & 1u) ? (d[w] & kMatMask) : 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            prefix += v;
+            t -= 32;
+            done = pref != 0u;
+        }
+        if (done) break;
+        if (retry) __nanosleep(40);
+    }
+    if (lane == 0) st_relaxed(desc + tile, kMatPrefix | ((prefix + total) & kMatMask));
+    return prefix;
+}
+
 // what the per-value helpers need of either parameter block
 struct FieldView {
     const uint64_t* index;
@@ -147,10 +189,9 @@ struct Unquoter {
     }
 };
 
-__device__ __forceinline__ uint64_t value_len(const FieldView& p, uint32_t r)
+// length of the value made of the raw slice [a, b)
+__device__ __forceinline__ uint64_t value_len_range(const FieldView& p, uint64_t a, uint64_t b)
 {
-    uint64_t a, b;
-    if (!field_range(p, r, a, b)) return 0;
     if (!trim_and_test(p, a, b)) return b - a;
     uint64_t o = 0;
     auto count = [&](uint32_t) { ++o; };
@@ -158,6 +199,82 @@ __device__ __forceinline__ uint64_t value_len(const FieldView& p, uint32_t r)
     scan_bytes(p.bytes, p.n, a, b, u);
     u.finish();
     return o;
+}
+
+__device__ __forceinline__ uint64_t value_len(const FieldView& p, uint32_t r)
+{
+    uint64_t a, b;
+    if (!field_range(p, r, a, b)) return 0;
+    return value_len_range(p, a, b);
+}
+
+constexpr int kMultiThreads = 256;
+constexpr int kColBatch = 4;
+constexpr uint32_t kColBatchMin = 8;   // columns from which the batched form pays
+
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// The dependent chain of one value is index slots -> first / last byte -> (only for padded or quoted values) a walk.
+// A thread that resolves the columns of its row issues each level for a batch of kColBatch columns before it uses any of
+// them: kColBatch loads in flight per thread instead of one round trip after another (1 GiB unquoted, 8 / 16 columns:
+// 3.43 -> 3.00 ms, 6.83 -> 4.82 ms; batches of 8 cost 80 registers and lose it again; the single-column kernels are
+// DRAM-sector-bound at 0.75-0.89 of peak and gain nothing from it).  ok bit k: the value exists;
+// plain bit k: neither end is padding and it is not a quoted field, so the value IS the raw slice [a, b).
+template <int kB>
+struct RangeBatch {
+    uint64_t a[kB], b[kB];
+    uint32_t ok, plain, quoted;   // quoted bit k: not padded, both ends are quotes: the value is the unquoted [a + 1, b - 1)
+};
+// item(k, rec, fld) -> does item k exist, and which (record, field) it is
+template <int kB, class Item>
+__device__ __forceinline__ void range_batch_load(const FieldView& p, Item item, RangeBatch<kB>& rb)
+{
+    rb.ok = rb.plain = rb.quoted = 0;
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+        rb.a[k] = rb.b[k] = 0;
+        uint32_t r = 0, f = 0;
+        if (!item(k, r, f)) continue;
+        if ((uint32_t)(r + 1u) >= p.record_cnt || f >= p.field_cnt) continue;
+        const uint32_t s = (uint32_t)(r + 1u) * p.row_size + f;   // u32 arithmetic, as the reference
+        if ((uint64_t)s + 1 >= p.index_len) continue;
+        rb.a[k] = ldg_u64(p.index + s);
+        rb.b[k] = ldg_u64(p.index + s + 1);
+        rb.ok |= 1u << k;
+    }
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+        if (!(rb.ok >> k & 1u)) continue;
+        rb.a[k] = rb.a[k] + 1 - p.pos_bias;
+        rb.b[k] = rb.b[k] - p.pos_bias;
+        if (!(rb.a[k] <= rb.b[k] && rb.b[k] <= p.n)) rb.ok &= ~(1u << k);
+    }
+    if (p.flags == 0u) {
+        rb.plain = rb.ok;
+        return;
+    }
+    uint32_t fb[kB], lb[kB];
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+        fb[k] = lb[k] = 0;
+        if ((rb.ok >> k & 1u) && rb.b[k] > rb.a[k]) {
+            fb[k] = ldg_u8(p.bytes + rb.a[k]);
+            lb[k] = ldg_u8(p.bytes + rb.b[k] - 1);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+        if (!(rb.ok >> k & 1u)) continue;
+        const bool padded = (p.flags & 2u) && (fb[k] == 0x20u || fb[k] == 0x09u || lb[k] == 0x20u || lb[k] == 0x09u);
+        const bool quoted = (p.flags & 1u) && rb.b[k] - rb.a[k] >= 2 && fb[k] == 0x22u && lb[k] == 0x22u;
+        if (rb.b[k] == rb.a[k] || (!padded && !quoted)) rb.plain |= 1u << k;
+        else if (!padded) rb.quoted |= 1u << k;
+    }
 }
 
 __global__ void __launch_bounds__(kMatThreads) materialize_offsets_kernel(const MaterializeParams p)
@@ -253,8 +370,19 @@ __global__ void __launch_bounds__(kMatThreads) materialize_write_kernel(const Ma
 // slots and bytes of neighbouring columns come out of the sectors the first column fetched.  Per column: a block scan
 // of the 256 lengths (warp w scans columns w, w + 8, ...), one decoupled look-back chain over the tile totals
 // (thread c looks back for column c), then the exclusive offsets go out coalesced.
-constexpr int kMultiThreads = 256;
+using ColBatch = RangeBatch<kColBatch>;
+__device__ __forceinline__ void col_batch_load(const MaterializeMultiParams& p, uint32_t r, uint32_t c0, bool row_live, ColBatch& cb)
+{
+    range_batch_load(view_of(p, 0), [&](int k, uint32_t& rec, uint32_t& fld) {
+        const uint32_t c = c0 + (uint32_t)k;
+        if (!row_live || c >= p.ncols) return false;
+        rec = r;
+        fld = p.field_idx[c];
+        return true;
+    }, cb);
+}
 
+template <bool kBatched>   // separate kernels: the batched form needs 64 registers, the plain one 32
 __global__ void __launch_bounds__(kMultiThreads) materialize_multi_offsets_kernel(const MaterializeMultiParams p)
 {
     extern __shared__ uint32_t s_len[];                    // [ncols][256] lengths, then exclusive prefixes in place
@@ -265,8 +393,32 @@ __global__ void __launch_bounds__(kMultiThreads) materialize_multi_offsets_kerne
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t i = (uint64_t)tile * kMultiThreads + tid;
-    for (uint32_t c = 0; c < p.ncols; ++c)
+    // fewer than kColBatchMin columns: one value after the other (the batches cost registers: 4 columns 1.86 -> 2.01 ms
+    // unquoted, 3.01 -> 3.29 ms quoted, where 8 / 16 unquoted columns go 3.43 -> 2.96 ms and 6.83 -> 4.74 ms)
+    for (uint32_t c = 0; !kBatched && c < p.ncols; ++c)
         s_len[c * kMultiThreads + tid] = i < p.nrec ? (uint32_t)value_len(view_of(p, c), p.first_record + (uint32_t)i) : 0u;
+    for (uint32_t c0 = 0; kBatched && c0 < p.ncols; c0 += kColBatch) {
+        ColBatch cb;
+        col_batch_load(p, p.first_record + (uint32_t)i, c0, i < p.nrec, cb);
+#pragma unroll
+        for (int k = 0; k < kColBatch; ++k) {
+            const uint32_t c = c0 + (uint32_t)k;
+            if (c >= p.ncols) break;
+            uint32_t len = 0;
+            if (cb.plain >> k & 1u)
+                len = (uint32_t)(cb.b[k] - cb.a[k]);
+            else if (cb.quoted >> k & 1u) {
+                uint32_t o = 0;
+                auto count = [&](uint32_t) { ++o; };
+                Unquoter<decltype(count)> u{count};
+                scan_bytes(p.bytes, p.n, cb.a[k] + 1, cb.b[k] - 1, u);
+                u.finish();
+                len = o;
+            } else if (cb.ok >> k & 1u)
+                len = (uint32_t)value_len_range(view_of(p, c), cb.a[k], cb.b[k]);          // padded: trim first
+            s_len[c * kMultiThreads + tid] = len;
+        }
+    }
     __syncthreads();
     for (uint32_t c = warp; c < p.ncols; c += kMultiThreads / 32) {
         uint32_t* col = s_len + c * kMultiThreads;
@@ -291,6 +443,9 @@ __global__ void __launch_bounds__(kMultiThreads) materialize_multi_offsets_kerne
         if (lane == 31) s_total[c] = inc;
     }
     __syncthreads();
+    // one chain per column, thread c walks column c's: all the chains of the tile advance together in one warp
+    // (a warp per chain with 128-descriptor hops, as the sweep below does, measured slower here: 0.404 against 0.362 ms
+    // for 8 columns, 0.697 against 0.513 ms for 16 -- with 256-row tiles the walks are short and the chains queue up)
     if (tid < p.ncols) {
         uint64_t* desc = p.tile_desc + (uint64_t)tid * p.tiles;
         const uint64_t total = s_total[tid];
@@ -318,12 +473,13 @@ __global__ void __launch_bounds__(kMultiThreads) materialize_multi_offsets_kerne
     }
 }
 
+template <bool kBatched>
 __global__ void __launch_bounds__(kMultiThreads) materialize_multi_write_kernel(const MaterializeMultiParams p)
 {
     const uint8_t* __restrict__ x = p.bytes;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.nrec) return;
-    for (uint32_t c = 0; c < p.ncols; ++c) {
+    for (uint32_t c = 0; !kBatched && c < p.ncols; ++c) {
         const FieldView fv = view_of(p, c);
         uint8_t* __restrict__ out = p.out[c];
         uint64_t a, b;
@@ -343,8 +499,52 @@ __global__ void __launch_bounds__(kMultiThreads) materialize_multi_write_kernel(
             u.finish();
         }
     }
+    for (uint32_t c0 = 0; kBatched && c0 < p.ncols; c0 += kColBatch) {
+        ColBatch cb;
+        col_batch_load(p, p.first_record + (uint32_t)i, c0, true, cb);
+        uint64_t o[kColBatch], o_end[kColBatch];
+#pragma unroll
+        for (int k = 0; k < kColBatch; ++k) {
+            o[k] = o_end[k] = 0;
+            if (cb.ok >> k & 1u) {
+                o[k] = p.offsets[c0 + k][i];
+                o_end[k] = p.offsets[c0 + k][i + 1];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kColBatch; ++k) {
+            const uint32_t c = c0 + (uint32_t)k;
+            if (c >= p.ncols) break;
+            if (!(cb.ok >> k & 1u) || o_end[k] > p.out_cap[c]) continue;   // the device form clips whole values
+            uint8_t* __restrict__ out = p.out[c];
+            uint64_t at = o[k];
+            auto put = [&](uint32_t ch) { out[at++] = (uint8_t)ch; };
+            uint64_t a = cb.a[k], b = cb.b[k];
+            if (cb.plain >> k & 1u) {
+                if (b - a < 16) {   // short raw values: a handful of byte loads beat 16 predicated steps per chunk
+                    for (; a < b; ++a) put(x[a]);
+                } else {
+                    scan_bytes(x, p.n, a, b, put);
+                }
+                continue;
+            }
+            if (cb.quoted >> k & 1u) {
+                Unquoter<decltype(put)> u{put};
+                scan_bytes(x, p.n, a + 1, b - 1, u);
+                u.finish();
+                continue;
+            }
+            const FieldView fv = view_of(p, c);
+            if (!trim_and_test(fv, a, b)) {
+                scan_bytes(x, p.n, a, b, put);
+            } else {
+                Unquoter<decltype(put)> u{put};
+                scan_bytes(x, p.n, a, b, u);
+                u.finish();
+            }
+        }
+    }
 }
-
 
 // ---- several columns, row sweep -------------------------------------------------------------------------------------
 // When the requested columns cover a fair share of every row, the cheapest way to fetch them is to stream the rows:
@@ -555,42 +755,8 @@ __global__ void __launch_bounds__(kSweepThreads) materialize_sweep_kernel(const 
                 if (lane == 0) s_gpre[c][k] = (uint32_t)total;
                 total += s_gtot[c][k];
             }
-            if (lane == 0) st_relaxed(desc + tile, kMatAgg | (total & kMatMask));
-            // Tiles are small (R rows), so tiles start faster than one 32-descriptor hop (~0.7 us of L2 latency) could
-            // follow: with one window per hop the nearest published prefix drifts away until every look-back walks all
-            // the tiles in flight.  Four windows are fetched at once per hop (128 tiles, loads overlapped).
-            uint64_t prefix = 0;
-            for (int64_t t = (int64_t)tile - 1; t >= 0;) {
-                uint64_t d[4];
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const int64_t mine = t - 32 * w - (int64_t)lane;
-                    d[w] = mine >= 0 ? ld_relaxed(desc + mine) : kMatPrefix;          // before tile 0: prefix 0
-                }
-                bool done = false, retry = false;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    if (done || retry) break;
-                    const uint32_t st = (uint32_t)(d[w] >> 62);
-                    const uint32_t pref = __ballot_sync(0xffffffffu, st == 2u), wait = __ballot_sync(0xffffffffu, st == 0u);
-                    const uint32_t upto = pref ? (uint32_t)__ffs((int)pref) - 1u : 31u;  // lanes 0 .. upto count
-                    const uint32_t use = 0xffffffffu >> (31u - upto);
-                    if (wait & use) {
-                        retry = true;                                                 // resume from this window
-                        break;
-                    }
-                    uint64_t v = (use >> lane & 1u) ? (d[w] & kMatMask) : 0ull;
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    prefix += v;
-                    t -= 32;
-                    done = pref != 0u;
-                }
-                if (done) break;
-                if (retry) __nanosleep(40);
-            }
+            const uint64_t prefix = lookback_warp(desc, tile, total, lane);
             if (lane == 0) {
-                st_relaxed(desc + tile, kMatPrefix | ((prefix + total) & kMatMask));
                 s_base[c] = prefix;
                 if (r0 + nr == p.nrec) p.offsets[c][p.nrec] = prefix + total;
             }
@@ -772,14 +938,21 @@ cudaError_t launch_materialize_multi_offsets(const MaterializeMultiParams& p, cu
 {
     if (p.tiles == 0 || p.ncols == 0) return cudaSuccess;
     const size_t smem = (size_t)p.ncols * kMultiThreads * sizeof(uint32_t);
-    materialize_multi_offsets_kernel<<<p.tiles, kMultiThreads, smem, stream>>>(p);
+    if (p.ncols >= kColBatchMin)
+        materialize_multi_offsets_kernel<true><<<p.tiles, kMultiThreads, smem, stream>>>(p);
+    else
+        materialize_multi_offsets_kernel<false><<<p.tiles, kMultiThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_materialize_multi_write(const MaterializeMultiParams& p, cudaStream_t stream)
 {
     if (p.nrec == 0 || p.ncols == 0) return cudaSuccess;
-    materialize_multi_write_kernel<<<(p.nrec + kMultiThreads - 1) / kMultiThreads, kMultiThreads, 0, stream>>>(p);
+    const unsigned blocks = (p.nrec + kMultiThreads - 1) / kMultiThreads;
+    if (p.ncols >= kColBatchMin)
+        materialize_multi_write_kernel<true><<<blocks, kMultiThreads, 0, stream>>>(p);
+    else
+        materialize_multi_write_kernel<false><<<blocks, kMultiThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
