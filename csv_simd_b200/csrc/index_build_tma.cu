@@ -50,8 +50,12 @@ constexpr uint32_t kInvalidTile = 0xffffffffu;
 //   kWorkers    worker warps per CTA (a sub-tile is kWorkers x 4 KiB; 16-bit staging offsets allow up to 16):
 //               the cost of the look-back chain grows with the number of CTAs in flight, so the same number
 //               of resident worker warps in fewer, larger CTAs shortens it
-template <int kMinBlocks_, int kStageBufs_, int kStageCap_, int kSub_, int kSkew_ = 1, int kWorkers_ = 8>
+template <int kMinBlocks_, int kStageBufs_, int kStageCap_, int kSub_, int kSkew_ = 1, int kWorkers_ = 8, int kExpand_ = 0>
 struct TmaShape {
+    // expansion loop: 0 = two entries per trip + a tail for the odd one; 1 = one loop whose second store is predicated
+    // (no tail, no trip count); 2 = 1 on sub-tiles with fewer than 3 entries per 32-byte group, else 0.  Measured (kv14 /
+    // kv15, 1 GiB): cfg2 0.3776 / 0.3791 / 0.3736 ms, cfg3 0.3416 / 0.3337 / 0.3318 ms for 0 / 1 / 2.
+    static constexpr int kExpand = kExpand_;
     static constexpr int kWorkers = kWorkers_;
     static constexpr int kWorkerThreads = kWorkers_ * 32;
     static constexpr int kThreadsAll = kWorkerThreads + 64;    // + TMA producer warp + look-back warp
@@ -71,8 +75,10 @@ struct TmaShape {
     static constexpr int kSlots = 2;                       // TMA ring depth in sub-tiles
 };
 using ShapeA = TmaShape<2, 2, 8192, 2>;          // 2 CTAs / SM, 99 KB each, 64 KiB per descriptor (round 1)
-using ShapeB = TmaShape<3, 1, 5120, 2>;          // 3 CTAs / SM, 75 KB each: one staging buffer (default since round 2)
-using ShapeH = TmaShape<2, 1, 7680, 2, 1, 12>;   // 2 CTAs / SM x 12 worker warps: 48 KiB sub-tiles, 96 KiB per descriptor
+using ShapeB = TmaShape<3, 1, 5120, 2, 1, 8, 2>; // 3 CTAs / SM, 75 KB each: one staging buffer (default since round 2)
+using ShapeH = TmaShape<2, 1, 7680, 2, 1, 12>;
+using ShapeN = TmaShape<3, 1, 5120, 2, 1, 8, 1>;   // B with the tail-less expansion loop everywhere (A/B)
+using ShapeP = TmaShape<3, 1, 5120, 2, 1, 8, 0>;   // B with the round-1 expansion loop everywhere (A/B)   // 2 CTAs / SM x 12 worker warps: 48 KiB sub-tiles, 96 KiB per descriptor
 // Measured on the 1 GiB configs, kernel ms cfg2 / cfg3 (gpurun_out kv2-kv6, round 2):
 //   A 0.395 / 0.346   B 0.391 / 0.342   H 0.401 / 0.344
 //   kSub = 4 (128 KiB per descriptor): 0.433 / 0.369 at 2 CTAs (36 pending mask registers), 0.539 / 0.453 at 3 (spills)
@@ -229,6 +235,7 @@ __device__ __forceinline__ void compact_sub(SmemTma<S>& sm, const BuildParams& p
     if (S::kStageBufs == 1) worker_barrier<S>();
     if (end <= kCap) {
         uint16_t* dst = stg + slot0;
+        const bool sparse = cnt < 3u * (uint32_t)(S::kTile / 32);   // fewer than 3 entries per 32-byte group on average
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) {
             uint32_t m = t.s[g] & ~(t.x[g] ^ flip);   // structure = all_struct & !string_mask (avx/stage1.rs:400-406)
@@ -237,6 +244,18 @@ __device__ __forceinline__ void compact_sub(SmemTma<S>& sm, const BuildParams& p
             // two entries per trip: immediate store offsets, one pointer bump, half the branches
             // (0.396 vs 0.403 ms on cfg2 against a one-entry loop; walking two groups per loop for more ILP
             //  measured slower, 0.439 ms: this phase is issue-bound)
+            if (S::kExpand == 1 || (S::kExpand == 2 && sparse)) {
+                uint16_t* d = dst;
+#pragma unroll 1
+                for (; m; d += 2) {
+                    d[0] = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
+                    m &= m - 1u;
+                    if (m) d[1] = (uint16_t)(rel0 + (uint32_t)__ffs((int)m) - 1u);
+                    m &= m - 1u;
+                }
+                dst += c;
+                continue;
+            }
 #pragma unroll 1
             for (uint32_t k = 0; k + 1u < c; k += 2u) {
                 const uint32_t b0 = (uint32_t)__ffs((int)m) - 1u;
@@ -698,6 +717,8 @@ cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream)
     switch ((p.tune >> 12) & 15u) {
     case 1: return launch_shape<ShapeA>(p, stream);
     case 7: return launch_shape<ShapeH>(p, stream);
+    case 13: return launch_shape<ShapeN>(p, stream);
+    case 14: return launch_shape<ShapeP>(p, stream);
     default: return launch_shape<ShapeB>(p, stream);
     }
 }
