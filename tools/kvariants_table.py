@@ -9,7 +9,7 @@ SHAPES = {0x1000: "A: 2 CTAs/SM, 95 regs, 2 staging buffers (round 1)", 0x2000: 
           0x3000: "D: A with 128 KiB per descriptor (kSub=4)", 0x4000: "E: B with kSub=4 (spills)",
           0x5000: "F: B with 2 super-tiles of skew (spills)", 0x6000: "G: A with 2 super-tiles of skew",
           0x7000: "H: 2 CTAs/SM x 12 worker warps (96 KiB per descriptor)", 0x8000: "I: 1 CTA/SM x 16 worker warps (128 KiB per descriptor)",
-          0x9000: "J: B without skew", 0xC000: "M: B with the transpose's right shifts on the FMA pipe (__umulhi)", 0xD000: "N: B with the tail-less expansion loop on every sub-tile", 0xE000: "O: B with the tail-less expansion loop on sparse sub-tiles (kv15; the default from kv16 on, where 0xE000 = P: B with the round-1 expansion loop)", 0xF000: "Q: default + sparse expansion loop from the highest bit down", 0xA000: "K: B with 32 KiB per descriptor (kSub=1)", 0xB000: "L: K without skew", 0: "default (B)"}
+          0x9000: "J: B without skew", 0xC000: "M: B with the transpose's right shifts on the FMA pipe (__umulhi)", 0xD000: "N: B with the tail-less expansion loop on every sub-tile", 0xE000: "O: B with the tail-less expansion loop on sparse sub-tiles (kv15; the default from kv16 on, where 0xE000 = P: B with the round-1 expansion loop)", 0xF000: "Q: default + sparse expansion loop from the highest bit down (kv16) / first two entries of a group without a loop (kv17)", 0xA000: "K: B with 32 KiB per descriptor (kSub=1)", 0xB000: "L: K without skew", 0: "default (B)"}
 
 
 def label(run: int, t: int) -> str:
