@@ -52,8 +52,8 @@ constexpr uint32_t kInvalidTile = 0xffffffffu;
 //               of resident worker warps in fewer, larger CTAs shortens it
 template <int kMinBlocks_, int kStageBufs_, int kStageCap_, int kSub_, int kSkew_ = 1, int kWorkers_ = 8, int kExpand_ = 0>
 struct TmaShape {
-    // expansion loop: 0 = two entries per trip + a tail for the odd one; 1 = one loop whose second store is predicated
-    // (no tail, no trip count); 2 = 1 on sub-tiles with fewer than 3 entries per 32-byte group, else 0.  Measured (kv14 /
+    // expansion loop: 0 = two entries per trip + a tail for the odd one; (1 = one loop whose second store is predicated,
+    // no tail, no trip count: measured, not kept;) 2 = that loop on sub-tiles with fewer than 3 entries per 32-byte group, else 0.  Measured (kv14 /
     // kv15, 1 GiB): cfg2 0.3776 / 0.3791 / 0.3736 ms, cfg3 0.3416 / 0.3337 / 0.3318 ms for 0 / 1 / 2.  Walking the bits
     // from the top (clz is one FLO where ffs is BREV + FLO) and filling the slots backwards: no change (kv16); the first
     // two entries of a group without a loop, the rest in one: 0.3496 against 0.3299 ms on cfg3 (kv17).
@@ -79,7 +79,6 @@ struct TmaShape {
 using ShapeA = TmaShape<2, 2, 8192, 2>;          // 2 CTAs / SM, 99 KB each, 64 KiB per descriptor (round 1)
 using ShapeB = TmaShape<3, 1, 5120, 2, 1, 8, 2>; // 3 CTAs / SM, 75 KB each: one staging buffer (default since round 2)
 using ShapeH = TmaShape<2, 1, 7680, 2, 1, 12>;
-using ShapeN = TmaShape<3, 1, 5120, 2, 1, 8, 1>;   // B with the tail-less expansion loop everywhere (A/B)
 using ShapeP = TmaShape<3, 1, 5120, 2, 1, 8, 0>;   // B with the round-1 expansion loop everywhere (A/B)   // 2 CTAs / SM x 12 worker warps: 48 KiB sub-tiles, 96 KiB per descriptor
 // Measured on the 1 GiB configs, kernel ms cfg2 / cfg3 (gpurun_out kv2-kv6, round 2):
 //   A 0.395 / 0.346   B 0.391 / 0.342   H 0.401 / 0.344
@@ -246,7 +245,7 @@ __device__ __forceinline__ void compact_sub(SmemTma<S>& sm, const BuildParams& p
             // two entries per trip: immediate store offsets, one pointer bump, half the branches
             // (0.396 vs 0.403 ms on cfg2 against a one-entry loop; walking two groups per loop for more ILP
             //  measured slower, 0.439 ms: this phase is issue-bound)
-            if (S::kExpand == 1 || (S::kExpand == 2 && sparse)) {
+            if (S::kExpand == 2 && sparse) {
                 uint16_t* d = dst;
 #pragma unroll 1
                 for (; m; d += 2) {
@@ -719,7 +718,6 @@ cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream)
     switch ((p.tune >> 12) & 15u) {
     case 1: return launch_shape<ShapeA>(p, stream);
     case 7: return launch_shape<ShapeH>(p, stream);
-    case 13: return launch_shape<ShapeN>(p, stream);
     case 14: return launch_shape<ShapeP>(p, stream);
     default: return launch_shape<ShapeB>(p, stream);
     }
