@@ -939,9 +939,15 @@ int pipeline_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint
     }();
     const bool two_threads = upload_thread && !o.d_bytes_in && n >= (64u << 20) && !is_pinned(host_bytes);
     std::thread uploader;
+    bool spawned = false;
     if (two_threads) {
-        uploader = std::thread(enqueue_all);
-    } else {
+        try {
+            uploader = std::thread(enqueue_all);
+            spawned = true;
+        } catch (...) {   // no thread to be had: enqueue on this one, as for pinned input
+        }
+    }
+    if (!spawned) {
         enqueue_all();
         rc = rc_up;
     }
