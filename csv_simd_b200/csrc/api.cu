@@ -203,6 +203,20 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
         p.shard_par = idx->d_shard_par;
         p.shard_rank = idx->shard_rank;
         p.tune = ctx->tune;
+        static const bool dbg_timeline = std::getenv("CSVB200_DBG_TIMELINE") != nullptr;
+        if (dbg_timeline && !redo && !idx->validate && !idx->ex) {   // debug: per-super-tile timestamps of this build
+            const size_t words = 8 * ((n + kTileBytes - 1) / kTileBytes + 1);
+            if (ctx->dbg_words < words) {
+                if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+                ctx->d_dbg = nullptr;
+                ctx->dbg_words = 0;
+                if (cudaMalloc((void**)&ctx->d_dbg, words * sizeof(uint64_t)) == cudaSuccess) ctx->dbg_words = words;
+            }
+            if (ctx->d_dbg) {
+                CU_TRY(ctx, cudaMemsetAsync(ctx->d_dbg, 0, ctx->dbg_words * sizeof(uint64_t), ctx->stream));
+                p.dbg = ctx->d_dbg;
+            }
+        }
         // kernel choice: the TMA pipeline for anything of size, the one-tile-per-CTA kernel for small
         // inputs; CSVB200_KERNEL=simple|tma forces one (tests cross-check the two against each other)
         bool use_tma = tma_path_usable(n);
@@ -525,6 +539,7 @@ void csvb200_ctx_destroy(csvb200_ctx* ctx)
     if (ctx->h_cells) cudaFreeHost(ctx->h_cells);
     delete ctx->pool;
     delete ctx->pool_down;
+    if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     for (int i = 0; i < 2; ++i) {
         if (ctx->h_bounce[i]) cudaFreeHost(ctx->h_bounce[i]);
         if (ctx->bounce_done[i]) cudaEventDestroy(ctx->bounce_done[i]);
@@ -591,6 +606,18 @@ int csvb200_host_free(void* p)
 {
     if (!p) return CSVB200_OK;
     return cudaFreeHost(p) == cudaSuccess ? CSVB200_OK : CSVB200_ERR_CUDA;
+}
+
+// Debug export (not part of include/csvb200.h): the timeline words of the last build made under CSVB200_DBG_TIMELINE.
+int csvb200_debug_timeline(csvb200_ctx* ctx, uint64_t* dst, size_t cap_words, size_t* words)
+{
+    if (!ctx || !words) return CSVB200_ERR_INVALID_ARG;
+    *words = ctx->dbg_words;
+    if (!dst || cap_words < ctx->dbg_words || !ctx->d_dbg) return ctx->d_dbg ? CSVB200_ERR_CAPACITY : CSVB200_ERR_INVALID_STATE;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaMemcpy(dst, ctx->d_dbg, ctx->dbg_words * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return CSVB200_OK;
 }
 
 int csvb200_host_register(void* p, size_t bytes, int read_only)

@@ -50,8 +50,11 @@ constexpr uint32_t kInvalidTile = 0xffffffffu;
 //   kWorkers    worker warps per CTA (a sub-tile is kWorkers x 4 KiB; 16-bit staging offsets allow up to 16):
 //               the cost of the look-back chain grows with the number of CTAs in flight, so the same number
 //               of resident worker warps in fewer, larger CTAs shortens it
-template <int kMinBlocks_, int kStageBufs_, int kStageCap_, int kSub_, int kSkew_ = 1, int kWorkers_ = 8, int kExpand_ = 0>
+template <int kMinBlocks_, int kStageBufs_, int kStageCap_, int kSub_, int kSkew_ = 1, int kWorkers_ = 8, int kExpand_ = 0, int kLook_ = 1>
 struct TmaShape {
+    // look-back: descriptors per lane and round trip (window = 32 * kLook; 64 / 128 measured slower in both rounds, also
+    // with the single-descriptor re-poll: kv18)
+    static constexpr int kLook = kLook_;
     // expansion loop: 0 = two entries per trip + a tail for the odd one; (1 = one loop whose second store is predicated,
     // no tail, no trip count: measured, not kept;) 2 = that loop on sub-tiles with fewer than 3 entries per 32-byte group, else 0.  Measured (kv14 /
     // kv15, 1 GiB): cfg2 0.3776 / 0.3791 / 0.3736 ms, cfg3 0.3416 / 0.3337 / 0.3318 ms for 0 / 1 / 2.  Walking the bits
@@ -296,15 +299,30 @@ __device__ __forceinline__ void compact_sub(SmemTma<S>& sm, const BuildParams& p
     }
 }
 
+__device__ __forceinline__ uint64_t dbg_clock()
+{
+    uint64_t c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+    return c;
+}
+__device__ __forceinline__ uint64_t dbg_globaltimer()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // compaction of the `it`-th super-tile this CTA processed
 // go_at: where this warp arrives on the producer's `go` barrier (see the producer): 0 = nowhere, 1 = as soon as the
 // prefix is there, 2 = after the first sub-tile's compaction, 3 = after the last one
-template <class S>
+template <class S, bool kDbg = false>
 __device__ __forceinline__ void compact_super(SmemTma<S>& sm, const BuildParams& p, const SuperRegs<S::kSub>& t, uint32_t it,
                                               uint32_t tid, uint32_t warp, uint32_t go_at)
 {
     const uint32_t pb = it % S::kRing;
+    if (kDbg && tid == 0) p.dbg[(uint64_t)t.tile * 8 + 2] = dbg_clock();      // the workers need the prefix from here
     mbar_wait(&sm.pref_full[pb], (it / S::kRing) & 1u);
+    if (kDbg && tid == 0) p.dbg[(uint64_t)t.tile * 8 + 3] = dbg_clock();      // ... and have it here
     if (go_at == 1u && (tid & 31u) == 0u) mbar_arrive(&sm.go);
     const PrefixInfo<S::kSub, S::kWorkers>& pi = sm.pref[pb];
 #pragma unroll
@@ -317,7 +335,7 @@ __device__ __forceinline__ void compact_super(SmemTma<S>& sm, const BuildParams&
 // kVal: CSVB200_BUILD_VALIDATE by-products; kEx: the cross-GPU exchange in the epilogue of the last CTA.  Both are
 // compile-time so that the plain build keeps the register allocation it was tuned with (with the exchange code merely
 // present the 64-register shape measured 0.401 instead of 0.391 ms on cfg2).
-template <class S, bool kVal, bool kEx>
+template <class S, bool kVal, bool kEx, bool kDbg = false>
 __global__ void __launch_bounds__(S::kThreadsAll, S::kMinBlocks)
 index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap tmap)
 {
@@ -368,6 +386,7 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 // puts the counter back to zero for the next launch on this scratch
                 if (tile == p.num_tiles + gridDim.x - 1u) *p.ticket = 0u;
                 if (tile >= p.num_tiles) tile = kInvalidTile;
+                if (kDbg && tile != kInvalidTile) p.dbg[(uint64_t)tile * 8 + 6] = dbg_clock();
 #pragma unroll
                 for (int sub = 0; sub < kSub; ++sub) {
                     const uint32_t sc = it * kSub + sub, st = sc % S::kSlots;
@@ -396,6 +415,13 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             mbar_wait(&sm.agg_full[b], (it / kRing) & 1u);
             const uint32_t tile = sm.agg_tile[b];
             if (tile == kInvalidTile) break;
+            if (kDbg && lane == 0) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                p.dbg[(uint64_t)tile * 8 + 0] = dbg_clock();                  // all aggregates of the super-tile are in
+                p.dbg[(uint64_t)tile * 8 + 4] = (uint64_t)smid | ((uint64_t)blockIdx.x << 16) | ((uint64_t)it << 32);
+                p.dbg[(uint64_t)tile * 8 + 5] = dbg_globaltimer();
+            }
             PrefixInfo<kSub, kWorkerWarps>& pi = sm.pref[b];
             // fold the kSub x 8 warp aggregates in file order; remember the state entering every warp
             // and the (parity, c0, c1) composite at every sub-tile boundary
@@ -436,7 +462,11 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
             uint64_t base;
             // one 32-descriptor window per round trip (wider windows measured slower both rounds: 0.400 / 0.427 ms
             // for 64 / 128 on cfg2 against 0.395 -- more polling traffic on the same lines)
-            decoupled_lookback<1>(p, tile, lane, pin, base);
+            decoupled_lookback<S::kLook, kDbg>(p, tile, lane, pin, base);
+            if (kDbg && lane == 0) {
+                p.dbg[(uint64_t)tile * 8 + 1] = dbg_clock();                  // the prefix is known
+                p.dbg[(uint64_t)tile * 8 + 7] = dbg_globaltimer();
+            }
             if (lane == 0) {
                 const uint32_t pend = pin ^ par;
                 const uint64_t cend = base + (pin ? o1 : o0);
@@ -591,20 +621,20 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
                 // no skew: the tile just classified is compacted at once (the other CTAs of the SM cover the look-back);
                 // nothing outlives an iteration, which frees the registers the pending masks take
                 if (cur.tile == kInvalidTile) break;
-                compact_super<S>(sm, p, cur, it, tid, warp, go_at);
+                compact_super<S, kDbg>(sm, p, cur, it, tid, warp, go_at);
                 continue;
             }
             // ---- ordered compaction of the super-tile classified kSkew iterations ago: its look-back has
             //      had kSkew classify phases to complete ----
             if (pend[0].tile != kInvalidTile)
-                compact_super<S>(sm, p, pend[0], it - kSkew, tid, warp, go_at);
+                compact_super<S, kDbg>(sm, p, pend[0], it - kSkew, tid, warp, go_at);
             else if (jit && lane == 0u)
                 mbar_arrive(&sm.go);   // nothing to compact yet: the producer may draw the next ticket at once
             if (cur.tile == kInvalidTile) {
                 // drain: the younger pending super-tiles, oldest first
 #pragma unroll
                 for (int k = 1; k < kSkew; ++k)
-                    if (pend[k].tile != kInvalidTile) compact_super<S>(sm, p, pend[k], it - kSkew + k, tid, warp, 0u);
+                    if (pend[k].tile != kInvalidTile) compact_super<S, kDbg>(sm, p, pend[k], it - kSkew + k, tid, warp, 0u);
                 break;
             }
 #pragma unroll
@@ -645,7 +675,7 @@ struct ShapeState {
     int grid_cap[kMaxDevices] = {};
 };
 
-template <class S, bool kVal = false, bool kEx = false>
+template <class S, bool kVal = false, bool kEx = false, bool kDbg = false>
 cudaError_t launch_shape(const BuildParams& p_in, cudaStream_t stream)
 {
     static ShapeState state;
@@ -672,14 +702,14 @@ cudaError_t launch_shape(const BuildParams& p_in, cudaStream_t stream)
     {
         std::lock_guard<std::mutex> lock(state.mu);
         if (state.grid_cap[dev] == 0) {
-            e = cudaFuncSetAttribute(index_build_tma_kernel<S, kVal, kEx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(index_build_tma_kernel<S, kVal, kEx, kDbg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(SmemTma<S>));
             if (e != cudaSuccess) return e;
-            cudaFuncSetAttribute(index_build_tma_kernel<S, kVal, kEx>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            cudaFuncSetAttribute(index_build_tma_kernel<S, kVal, kEx, kDbg>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
             int sms = 148, per_sm = 0;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, index_build_tma_kernel<S, kVal, kEx>, S::kThreadsAll,
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, index_build_tma_kernel<S, kVal, kEx, kDbg>, S::kThreadsAll,
                                                               sizeof(SmemTma<S>));
             if (e != cudaSuccess) return e;
             if (per_sm < 1) return cudaErrorLaunchOutOfResources;
@@ -698,7 +728,7 @@ cudaError_t launch_shape(const BuildParams& p_in, cudaStream_t stream)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = p.pdl_wait ? 1u : 0u;
-    return cudaLaunchKernelEx(&cfg, index_build_tma_kernel<S, kVal, kEx>, p, tmap);
+    return cudaLaunchKernelEx(&cfg, index_build_tma_kernel<S, kVal, kEx, kDbg>, p, tmap);
 }
 
 }  // namespace
@@ -714,6 +744,7 @@ cudaError_t launch_index_build_tma(const BuildParams& p, cudaStream_t stream)
 {
     if (p.validate) return p.ex.peers ? launch_shape<ShapeB, true, true>(p, stream) : launch_shape<ShapeB, true, false>(p, stream);
     if (p.ex.peers) return launch_shape<ShapeB, false, true>(p, stream);
+    if (p.dbg) return launch_shape<ShapeB, false, false, true>(p, stream);   // timeline instrumentation (tools/timeline.py)
     // CSVB200_TUNE bits 12-15 force a shape (A/B of the shapes on the same box); 0 = the default
     switch ((p.tune >> 12) & 15u) {
     case 1: return launch_shape<ShapeA>(p, stream);

@@ -194,10 +194,21 @@ __device__ __forceinline__ void exchange_if_last(const BuildParams& p)
 // nearest published prefix is typically one "wave" (= number of resident CTAs) of tiles back; a
 // window that covers the whole wave resolves the look-back in about one L2 round trip instead of
 // wave / 32 serial ones (ncu: >50 % of worker stalls were waits on this chain with a 64-tile window).
-template <int kLookbackPerLane>
+// Measured with tools/timeline.py (round 2, 1 GiB quote-heavy, 444 CTAs, a ticket every ~16 ns): a look-back takes 6.5-7.2 us
+// -- about the slack one super-tile of skew gives it (7.3 us), so 40-50 % of the tiles make their workers wait, 0.75-1 us
+// on average = 8-11 % of the kernel.  It is 6.5 round trips of 1.1 us each (L2 latency under the streaming load), of which
+// 3.9 are retries: the aggregates of the tiles just before ours arrive on average 2.7 us AFTER our own (max of the 64
+// before us; ticket -> aggregates takes 5.9 us +- 1.3).  Tried on that evidence, all slower or equal: a two-level walk
+// (a tile with no prefix in its window publishes the composite of [tile - 32, tile]; later round trips read 32 such
+// spans = 1056 tiles at once: 2 forward trips instead of 2.6 but more retries, 0.342 against 0.330 ms); every lane
+// waiting for its own descriptor (no retries, 2.7 trips of 2.8 us: 0.337); 64 / 128 descriptors per trip with and
+// without the single-descriptor re-poll (0.338 / 0.373).  What is left is inherent to one pass: prefix(t) needs the
+// slowest of the ~100 tiles in flight before t.
+template <int kLookbackPerLane, bool kDbg = false>
 __device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_t tile, uint32_t lane, uint32_t& pin_out,
                                                    uint64_t& base_out)
 {
+    uint32_t dbg_trips = 0, dbg_polls = 0;   // (kDbg) round trips in all, of which retries of a window
     auto virtual_prefix = [&]() -> uint64_t { return virtual_prefix_desc(p); };
 
     // Suffix composite S = (sp, sc0, sc1) of the tiles already absorbed (those nearest to us).
@@ -211,6 +222,7 @@ __device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_
     uint32_t pin = 0u;
     uint64_t base = 0ull;
     while (true) {
+        if (kDbg) ++dbg_trips;
         uint64_t d[kLookbackPerLane];
 #pragma unroll
         for (int j = 0; j < kLookbackPerLane; ++j) {
@@ -244,7 +256,8 @@ __device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_
         const uint32_t ls = stopped ? (uint32_t)(__ffs(stopped) - 1) : 32u;   // nearest lane that stopped
         const uint32_t ls_stop = __shfl_sync(0xffffffffu, stop, (int)(ls & 31u));
         if (ls < 32u && ls_stop == 1u) {   // an unpublished tile lies before the nearest prefix: poll again
-            if (p.tune & 1u) {
+            if (kDbg) ++dbg_polls;
+            if (!(p.tune & 1u)) {   // default since kv18 / kv20 (0.3-1.1 % on both 1 GiB inputs); CSVB200_TUNE bit 1: re-poll the window (A/B)
                 // wait on THAT descriptor alone (one line instead of the whole window per poll: hundreds of look-back
                 // warps poll at the same time and their traffic competes with the data streams in L2), then rescan
                 const int64_t widx = idx0 - (int64_t)ls * kLookbackPerLane - (kLookbackPerLane - 1);
@@ -285,6 +298,7 @@ __device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_
     }
     pin_out = pin;
     base_out = base;
+    if (kDbg && lane == 0) p.dbg[(uint64_t)tile * 8 + 6] |= ((uint64_t)dbg_trips << 48) | ((uint64_t)dbg_polls << 56);   // clock64 of the ticket keeps 48 bits
 }
 
 }  // namespace csvb200

@@ -87,6 +87,7 @@ struct BuildParams {
     const uint32_t* shard_par;
     uint32_t shard_rank;
     uint32_t tune;           // experiment knob (CSVB200_TUNE)
+    uint64_t* dbg;           // debug timeline (CSVB200_DBG_TIMELINE): 8 words per super-tile, see tools/timeline.py; null normally
     // speculative multi-GPU build: when non-null the launch is a conditional redo and exits at once
     // unless *run_flag != 0 (the carry prediction turned out wrong)
     const uint32_t* run_flag;

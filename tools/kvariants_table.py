@@ -9,7 +9,7 @@ SHAPES = {0x1000: "A: 2 CTAs/SM, 95 regs, 2 staging buffers (round 1)", 0x2000: 
           0x3000: "D: A with 128 KiB per descriptor (kSub=4)", 0x4000: "E: B with kSub=4 (spills)",
           0x5000: "F: B with 2 super-tiles of skew (spills)", 0x6000: "G: A with 2 super-tiles of skew",
           0x7000: "H: 2 CTAs/SM x 12 worker warps (96 KiB per descriptor)", 0x8000: "I: 1 CTA/SM x 16 worker warps (128 KiB per descriptor)",
-          0x9000: "J: B without skew", 0xC000: "M: B with the transpose's right shifts on the FMA pipe (__umulhi)", 0xD000: "N: B with the tail-less expansion loop on every sub-tile", 0xE000: "O: B with the tail-less expansion loop on sparse sub-tiles (kv15; the default from kv16 on, where 0xE000 = P: B with the round-1 expansion loop)", 0xF000: "Q: default + sparse expansion loop from the highest bit down (kv16) / first two entries of a group without a loop (kv17)", 0xA000: "K: B with 32 KiB per descriptor (kSub=1)", 0xB000: "L: K without skew", 0: "default (B)"}
+          0x9000: "J: B without skew", 0xC000: "M: B with the transpose's right shifts on the FMA pipe (__umulhi)", 0xD000: "N: B with the tail-less expansion loop on every sub-tile", 0xE000: "O: B with the tail-less expansion loop on sparse sub-tiles (kv15; the default from kv16 on, where 0xE000 = P: B with the round-1 expansion loop)", 0xA000 if False else 0x10000: "", 0xF000: "Q: default + sparse expansion loop from the highest bit down (kv16) / first two entries of a group without a loop (kv17)", 0xA000: "K: B with 32 KiB per descriptor (kSub=1)", 0xB000: "L: K without skew", 0: "default (B)"}
 
 
 def label(run: int, t: int) -> str:
@@ -17,11 +17,19 @@ def label(run: int, t: int) -> str:
         return SHAPES[0x1000] if t == 256 else SHAPES[0x2000]
     shape, m = t & 0xF000, t & 0xFFF
     nm = SHAPES.get(shape, hex(shape))
+    if run == 18 and shape in (0xA000, 0xB000):
+        nm = "B with %d descriptors per look-back round trip" % (128 if shape == 0xA000 else 64)
+    if run == 19 and shape == 0xA000:
+        nm = "B with the two-level look-back (a tile without a prefix in its window publishes the composite of 33 tiles)"
     if run <= 7:   # before the just-in-time tickets: low bits = look-back knobs
         if m in (1, 2, 3):
             nm += " + " + {1: "re-poll one descriptor", 2: "look-back window 64", 3: "look-back window 128"}[m]
     else:          # kv8+: tickets are just-in-time by default; bit 4 = round-1 ticket policy, bits 8 / 16 = where `go` is signalled
         nm += " + JIT tickets" if not (m & 4) else " + tickets drawn when a ring slot frees (round 1)"
+        if 18 <= run <= 20 and (m & 3):
+            nm += {1: ", re-poll one descriptor (the default after kv20)", 2: ", every lane waits for its own descriptor", 3: "?"}[m & 3]
+        if run >= 21:
+            nm += ", re-poll the whole window (the default up to kv20)" if (m & 1) else ", re-poll one descriptor"
         if (m & 24) == 8:
             nm += ", go right after the prefix wait"
         if (m & 24) == 16:
