@@ -202,8 +202,9 @@ __device__ __forceinline__ void exchange_if_last(const BuildParams& p)
 // (a tile with no prefix in its window publishes the composite of [tile - 32, tile]; later round trips read 32 such
 // spans = 1056 tiles at once: 2 forward trips instead of 2.6 but more retries, 0.342 against 0.330 ms); every lane
 // waiting for its own descriptor (no retries, 2.7 trips of 2.8 us: 0.337); 64 / 128 descriptors per trip with and
-// without the single-descriptor re-poll (0.338 / 0.373).  What is left is inherent to one pass: prefix(t) needs the
-// slowest of the ~100 tiles in flight before t.
+// without the single-descriptor re-poll (0.338 / 0.373); a look-back warp that has resolved its tile also publishing the
+// prefixes of the next tiles whose aggregates are in (idempotent forward push: 0.333 against 0.331, kv22).  What is left
+// is inherent to one pass: prefix(t) needs the slowest of the ~100 tiles in flight before t.
 template <int kLookbackPerLane, bool kDbg = false>
 __device__ __forceinline__ void decoupled_lookback(const BuildParams& p, uint32_t tile, uint32_t lane, uint32_t& pin_out,
                                                    uint64_t& base_out)

@@ -19,6 +19,8 @@ def label(run: int, t: int) -> str:
     nm = SHAPES.get(shape, hex(shape))
     if run == 18 and shape in (0xA000, 0xB000):
         nm = "B with %d descriptors per look-back round trip" % (128 if shape == 0xA000 else 64)
+    if run == 22 and shape == 0xA000:
+        nm = "B + forward push (a resolved tile publishes the prefixes of the tiles after it whose aggregates are in)"
     if run == 19 and shape == 0xA000:
         nm = "B with the two-level look-back (a tile without a prefix in its window publishes the composite of 33 tiles)"
     if run <= 7:   # before the just-in-time tickets: low bits = look-back knobs
