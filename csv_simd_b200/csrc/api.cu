@@ -261,6 +261,10 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
                 p.total_out = reinterpret_cast<unsigned long long*>(idx->d_result2 + 3);
             }
         }
+        // the conditional re-index of the exchange form sits right behind the build: launched programmatically
+        // dependent, its CTAs are scheduled as the build's CTAs leave, wait for the build's completion inside the kernel and
+        // exit on the flag -- the launch latency hides behind the build's tail (CSVB200_TUNE bit 0x800: plain stream order)
+        if (redo && idx->ex && use_tma && ctx->host_result && !(ctx->tune & 0x800u)) p.pdl_wait = 2u;
         if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
         if (idx->speculative && !redo && !idx->verified) {
             // predicted carry-in parity (rank 0 and empty shards: known to be 0) into the device cell the launch reads;

@@ -348,7 +348,12 @@ index_build_tma_kernel(const BuildParams p, const __grid_constant__ CUtensorMap 
     const bool jit = (p.tune & 4u) == 0u;   // CSVB200_TUNE bit 4: draw tickets as soon as a ring slot frees (round 1; A/B)
     const uint32_t go_at = !jit ? 0u : ((p.tune >> 3) & 3u) == 1u ? 1u : ((p.tune >> 3) & 3u) == 2u ? 3u : 2u;   // A/B: bits 8, 16
 
-    if (p.run_flag != nullptr && *p.run_flag == 0u) return;   // conditional redo that is not needed
+    if (p.run_flag != nullptr) {   // conditional redo
+        if (p.pdl_wait == 2u) asm volatile("griddepcontrol.wait;" ::: "memory");   // launched under the build: its flag is final now
+        if (*p.run_flag == 0u) return;                                              // ... and says it is not needed
+    }
+    // exchange form: the conditional redo behind this launch may be scheduled as soon as our CTAs leave
+    if (kEx && tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (tid == 0) {
 #pragma unroll
