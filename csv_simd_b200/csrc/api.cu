@@ -208,6 +208,8 @@ int enqueue_build(csvb200_index* idx, bool timed, bool redo = false)
             const size_t words = 8 * ((n + kTileBytes - 1) / kTileBytes + 1);
             if (ctx->dbg_words < words) {
                 if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+    if (ctx->h_small_in) cudaFreeHost(ctx->h_small_in);
+    if (ctx->h_small_out) cudaFreeHost(ctx->h_small_out);
                 ctx->d_dbg = nullptr;
                 ctx->dbg_words = 0;
                 if (cudaMalloc((void**)&ctx->d_dbg, words * sizeof(uint64_t)) == cudaSuccess) ctx->dbg_words = words;
@@ -825,6 +827,62 @@ static int build_to_host_serial(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
     return rc;
 }
 
+// Small inputs (<= 256 KiB): the call is all latency -- two copies, a stream-ordered allocation, two synchronisations
+// around a ~5 us kernel cost 46-63 us, while the reference's loop indexes 64 KiB in 10 us.  Here the kernel reads the
+// bytes straight out of pinned host memory and writes the entries straight into pinned host memory (zero-copy over
+// PCIe; both buffers are the context's own and reused, or the caller's destination when that is pinned): one launch, one
+// synchronisation, no device allocation.  CSVB200_SMALL_DIRECT=0 takes the general path (A/B, tests).
+constexpr size_t kSmallDirectBytes = 256u << 10;
+static int build_to_host_small(csvb200_ctx* ctx, const uint8_t* host_bytes, size_t n, uint64_t* dst, size_t dst_cap,
+                               size_t* len_out)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->h_small_in) {
+        CU_TRY(ctx, cudaHostAlloc((void**)&ctx->h_small_in, kSmallDirectBytes + 64, cudaHostAllocMapped));
+        CU_TRY(ctx, cudaHostAlloc((void**)&ctx->h_small_out, (kSmallDirectBytes + 2) * sizeof(uint64_t), cudaHostAllocMapped));
+    }
+    std::memcpy(ctx->h_small_in, host_bytes, n);
+    bool direct = is_pinned(dst) && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0;
+    void* dst_dev = nullptr;
+    if (direct && (cudaHostGetDevicePointer(&dst_dev, dst, 0) != cudaSuccess || dst_dev != static_cast<void*>(dst))) {
+        cudaGetLastError();
+        direct = false;   // pinned, but not addressable from the device under the same pointer: stage it
+    }
+    uint64_t* out = direct ? dst : ctx->h_small_out;
+    const size_t cap = direct ? dst_cap : kSmallDirectBytes + 2;
+    CellLease lease(ctx, 1);
+    if (!lease.ok()) return fail(ctx, CSVB200_ERR_OOM, "no free result cell (4095 live index objects)");
+    uint64_t* d_cell = ctx->d_cells + lease.first * kCellWords;
+    uint64_t* h_cell = ctx->h_cells + lease.first * kCellWords;
+    const uint64_t num_tiles = (n + kTileBytes - 1) / kTileBytes;
+    uint32_t tag = 0;
+    int rc = next_build_scratch(ctx, 128 + num_tiles * kDescStride * sizeof(uint64_t), ctx->stream, &tag);
+    if (rc) return rc;
+    BuildParams p{};
+    p.desc_tag = tag;
+    p.in = ctx->h_small_in;       // unified addressing: pinned host memory is addressable from the device as it is
+    p.n = n;
+    p.index = out;
+    p.cap = cap;
+    p.out_base = 1;
+    p.write_sentinel = 1u;
+    p.num_tiles = (uint32_t)num_tiles;
+    p.ticket = reinterpret_cast<uint32_t*>(ctx->d_bscratch);
+    p.desc = reinterpret_cast<uint64_t*>(ctx->d_bscratch + 128);
+    p.result = d_cell;
+    p.result_host = h_cell;
+    p.result2_words = 2;
+    p.tune = ctx->tune;
+    CU_TRY(ctx, launch_index_build(p, ctx->stream));
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t len = 1 + (size_t)h_cell[0];
+    *len_out = len;
+    if (len > dst_cap) return fail(ctx, CSVB200_ERR_CAPACITY, "destination index buffer too small");
+    if (!direct) std::memcpy(dst, ctx->h_small_out, len * sizeof(uint64_t));
+    return CSVB200_OK;
+}
+
 // End-to-end pipeline: the input goes up in e2e_chunk pieces, each piece is indexed by its own launch
 // chained to the previous one through a device-resident carry cell {entries so far, quote parity}
 // (no host round trip between launches), and every finished index segment goes down on a second
@@ -1065,6 +1123,11 @@ int csvb200_index_build_to_host(csvb200_ctx* ctx, const uint8_t* host_bytes, siz
                                 size_t* len_out)
 {
     if (!ctx || !len_out || (n && !host_bytes)) return fail(ctx, CSVB200_ERR_INVALID_ARG, "null argument");
+    static const bool small_direct = [] {
+        const char* e = std::getenv("CSVB200_SMALL_DIRECT");
+        return !(e && e[0] == '0');
+    }();
+    if (small_direct && n > 0 && n <= kSmallDirectBytes && dst && ctx->kernel_override != 2) return build_to_host_small(ctx, host_bytes, n, dst, dst_cap, len_out);
     const size_t nchunks = (n + ctx->e2e_chunk - 1) / ctx->e2e_chunk;
     if (nchunks < 2 || nchunks + 1 >= kRingCells || !dst) return build_to_host_serial(ctx, host_bytes, n, dst, dst_cap, len_out);
     bool overflow = false;

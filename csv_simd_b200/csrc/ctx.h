@@ -52,6 +52,8 @@ struct csvb200_ctx {
     cudaEvent_t bounce_done[2] = {nullptr, nullptr};
     csvb200::SlicePool* pool = nullptr;   // host threads for pread / staging copies, created on first use (io_pool)
     csvb200::SlicePool* pool_down = nullptr;   // a second set for the download side of the pageable pipeline (io_pool_down)
+    uint8_t* h_small_in = nullptr;             // pinned, device-mapped staging of the small-input fast path (build_to_host_small)
+    uint64_t* h_small_out = nullptr;
     uint64_t* d_dbg = nullptr;                 // CSVB200_DBG_TIMELINE: 8 words per super-tile of the last device-resident build
     size_t dbg_words = 0;
     int io_threads = 0;                        // slices per pool; 0 = default_io_threads() (csvb200_multi_create divides them over its devices)

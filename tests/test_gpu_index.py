@@ -650,6 +650,36 @@ def test_materialize_columns_row_sweep_and_per_row_paths(ctx, flags, sweep, monk
     idx.free()
 
 
+def test_build_to_host_small_inputs_zero_copy(ctx):
+    """csvb200_index_build_to_host at <= 256 KiB: the kernel reads and writes pinned host memory directly (one launch, one
+    synchronisation).  Every edge case of tests/cases.py plus sizes around the 32 KiB tile and the 256 KiB limit, into
+    pageable and pinned destinations, a destination that is too small, and a dense input (one entry per byte)."""
+    import torch
+    rng = np.random.default_rng(11)
+    inputs = [raw for _, raw in cases.edge_cases() + cases.small_cases() if 0 < len(raw) <= (256 << 10)]
+    q, _ = gen.quoted(300 << 10, seed=52)
+    for size in (1, 63, 64, 65, 32767, 32768, 32769, 65536 + 5, (256 << 10) - 1, 256 << 10):
+        inputs.append(q[:size].tobytes())
+    inputs.append(b"," * 70000)                                   # one entry per byte
+    inputs.append(bytes(rng.choice(np.frombuffer(b'a,"\n\r ', dtype=np.uint8), size=100000)))
+    h_out = torch.zeros((256 << 10) + 64, dtype=torch.int64).pin_memory()
+    for raw in inputs:
+        a = np.frombuffer(raw, dtype=np.uint8)
+        want = O.read_sse(a) if a.size >= 64 else O.read_closed_form(a, 0, 0, with_sentinel=True)[0]
+        out = np.zeros(want.size + 8, dtype=np.uint64)
+        ln = ctx.index_build_to_host(a.ctypes.data, a.size, out.ctypes.data, out.size)              # pageable destination
+        assert ln == want.size and (out[:ln] == want).all(), len(raw)
+        h_out.zero_()
+        ln = ctx.index_build_to_host(a.ctypes.data, a.size, h_out.data_ptr(), h_out.numel())        # pinned: written in place
+        assert ln == want.size and (h_out.numpy()[:ln].view(np.uint64) == want).all(), len(raw)
+        assert (h_out.numpy()[ln:ln + 8] == 0).all()
+        if want.size > 3:
+            h_out.zero_()
+            with pytest.raises(BufferError):                      # CSVB200_ERR_CAPACITY
+                ctx.index_build_to_host(a.ctypes.data, a.size, h_out.data_ptr(), want.size - 2)
+            assert (h_out.numpy()[want.size - 2:want.size + 8] == 0).all()   # nothing past the capacity is written
+
+
 def test_host_register_pins_caller_memory(ctx):
     """csvb200_host_register: an ordinary array becomes DMA-able in place (the end-to-end call takes its pinned branch),
     the result equals the oracle's, a second registration of the same range is refused, unregister restores it."""
