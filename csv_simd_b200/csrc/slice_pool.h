@@ -138,8 +138,16 @@ enum class CopyDir { ToStaging, ToCaller };
 inline void parallel_memcpy(SlicePool& pool, void* dst, const void* src, size_t bytes, CopyDir dir = CopyDir::ToCaller)
 {
     const bool nt = (stream_copy_mask() & (dir == CopyDir::ToStaging ? 1 : 2)) != 0;
-    if (bytes < (4u << 20)) {
-        std::memcpy(dst, src, bytes);
+    static const size_t min_parallel = [] {
+        const char* e = std::getenv("CSVB200_PARALLEL_COPY_MIN");   // bytes from which a copy is sliced over the pool (A/B)
+        const long v = e ? std::atol(e) : 0;
+        return v > 0 ? (size_t)v : (size_t)(1u << 20);
+    }();
+    if (bytes < min_parallel) {
+        if (nt)
+            stream_memcpy(dst, src, bytes);
+        else
+            std::memcpy(dst, src, bytes);
         return;
     }
     pool.run([&](int i, int n) {
